@@ -1,0 +1,89 @@
+"""In-tree build of libipn_b200.so (nvcc, sm_100a only).  Used by ``__graft_entry__.build()`` and ``make``.
+
+The library is built next to this file (``pyipn_b200/libipn_b200.so``) so that it travels with the repo
+snapshot to the GPU box; it is git-ignored.  No JIT, no torch extension machinery: plain ``nvcc -shared``.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libipn_b200.so")
+OBJDIR = os.path.join(CSRC, "build")
+
+SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libipn_b200 cannot be built (there is no CPU fallback)")
+
+
+def _stamp(sources) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, name), "rb") as f:
+                    h.update(name.encode())
+                    h.update(f.read())
+    return h.hexdigest()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    os.makedirs(OBJDIR, exist_ok=True)
+    stamp_file = os.path.join(OBJDIR, "stamp")
+    stamp = _stamp(sources)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    nvcc = _nvcc()
+    log_path = os.path.join(OBJDIR, "ptxas.log")
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    objs, logs = [], []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        for src, obj, r in ex.map(compile_one, sources):
+            logs.append(f"==== {src} ====\n{r.stdout}\n{r.stderr}")
+            if r.returncode != 0:
+                sys.stderr.write(logs[-1])
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(obj)
+    with open(log_path, "w") as f:
+        f.write("\n".join(logs))
+    if verbose:
+        sys.stderr.write("\n".join(logs))
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed")
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

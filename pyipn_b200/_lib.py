@@ -1,0 +1,260 @@
+"""ctypes binding of libipn_b200.so (the C ABI declared in include/ipn.h).
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible, every compute entry
+point raises ``IpnError`` -- loudly -- instead of computing anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libipn_b200.so")
+
+IPN_OK = 0
+IPN_ERR_INVALID_ARGUMENT = -1
+IPN_ERR_NO_DEVICE = -2
+IPN_ERR_CUDA = -3
+IPN_ERR_ALLOC = -4
+IPN_ERR_UNSUPPORTED = -5
+
+OPT_LOGLIK_IMPL = 1
+OPT_PRECISE_W = 2
+OPT_DRAW_BATCH = 3
+
+# every symbol include/ipn.h declares (tests/test_abi.py checks the list against the header and the .so)
+EXPORTS = (
+    "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
+    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_last_error", "ipn_version",
+    "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
+    "ipn_loglik_sky_grid", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
+)
+
+
+class IpnError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libipn_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_p = C.c_void_p
+_i64 = C.c_int64
+
+
+def load_library():
+    """Load (once) and return the ctypes handle; raises IpnError if the CUDA library has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise IpnError(
+                IPN_ERR_NO_DEVICE,
+                f"{LIB_PATH} not found: build it with `python -m pyipn_b200._build` "
+                "(pyipn_b200 has no CPU fallback and will not compute without its CUDA library)",
+            )
+        lib = C.CDLL(LIB_PATH)
+        lib.ipn_last_error.restype = C.c_char_p
+        lib.ipn_version.restype = C.c_char_p
+        lib.ipn_ctx_create.argtypes = [C.c_int, C.POINTER(_p)]
+        lib.ipn_ctx_destroy.argtypes = [_p]
+        lib.ipn_ctx_destroy.restype = None
+        lib.ipn_ctx_set_stream.argtypes = [_p, _p]
+        lib.ipn_ctx_synchronize.argtypes = [_p]
+        lib.ipn_ctx_set_option.argtypes = [_p, C.c_int, _i64]
+        lib.ipn_ctx_launch_count.argtypes = [_p]
+        lib.ipn_ctx_launch_count.restype = C.c_uint64
+        lib.ipn_ctx_last_kernel_ms.argtypes = [_p]
+        lib.ipn_ctx_last_kernel_ms.restype = C.c_double
+        rff_args = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]
+        lib.ipn_rff_eval.argtypes = rff_args
+        lib.ipn_rff_eval_dev.argtypes = rff_args
+        grid_args = [_p, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p]
+        lib.ipn_loglik_delay_grid.argtypes = grid_args
+        lib.ipn_loglik_delay_grid_dev.argtypes = grid_args
+        lib.ipn_loglik_sky_grid.argtypes = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]
+        pc_args = [_p, _i64, _p, _i64, _p, _p, C.c_uint64, _p]
+        lib.ipn_poisson_counts.argtypes = pc_args
+        lib.ipn_poisson_counts_dev.argtypes = pc_args
+        lib.ipn_microbench.argtypes = [_p, C.c_int, C.POINTER(C.c_double)]
+        _lib = lib
+        return lib
+
+
+def _check(lib, rc):
+    if rc != IPN_OK:
+        raise IpnError(rc, lib.ipn_last_error().decode("utf-8", "replace"))
+
+
+def _f64(x, shape=None, name="array"):
+    arr = np.ascontiguousarray(x, dtype=np.float64)
+    if shape is not None and tuple(arr.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(arr.shape)}")
+    return arr
+
+
+def _ptr(arr):
+    return C.c_void_p(arr.ctypes.data)
+
+
+class Context:
+    """One libipn_b200 context = one GPU.  Host-array methods take/return numpy; ``*_dev`` take raw device pointers."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = _p()
+        _check(self._lib, self._lib.ipn_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ipn_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None):
+        _check(self._lib, self._lib.ipn_ctx_set_stream(self._h, _p(cuda_stream or 0)))
+
+    def synchronize(self):
+        _check(self._lib, self._lib.ipn_ctx_synchronize(self._h))
+
+    def set_option(self, key: int, value: int):
+        _check(self._lib, self._lib.ipn_ctx_set_option(self._h, int(key), int(value)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ipn_ctx_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.ipn_ctx_last_kernel_ms(self._h))
+
+    def microbench(self, which: int) -> float:
+        out = C.c_double(0.0)
+        _check(self._lib, self._lib.ipn_microbench(self._h, int(which), C.byref(out)))
+        return out.value
+
+    # ---- host-array entry points -----------------------------------------------------------------------
+    def rff_eval(self, time, omega, a, b, shift, amp):
+        time = _f64(time).ravel()
+        omega = np.atleast_2d(_f64(omega))
+        S, J = omega.shape
+        a = _f64(a, (S, J), "a") if np.ndim(a) == 2 else _f64(np.atleast_2d(a), (S, J), "a")
+        b = _f64(b, (S, J), "b") if np.ndim(b) == 2 else _f64(np.atleast_2d(b), (S, J), "b")
+        shift = _f64(np.atleast_1d(shift), (S,), "shift")
+        amp = _f64(np.atleast_1d(amp), (S,), "amp")
+        out = np.empty((S, time.size), dtype=np.float64)
+        _check(self._lib, self._lib.ipn_rff_eval(self._h, time.size, _ptr(time), S, J, _ptr(omega), _ptr(a), _ptr(b),
+                                                  _ptr(shift), _ptr(amp), _ptr(out)))
+        return out
+
+    def loglik_delay_grid(self, time, exposure, counts, omega, a, b, amp, bkg, delays, out=None):
+        time = _f64(time).ravel()
+        T = time.size
+        exposure = _f64(exposure, (T,), "exposure")
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        if counts.shape != (T,):
+            raise ValueError(f"counts: expected shape {(T,)}, got {counts.shape}")
+        omega = np.atleast_2d(_f64(omega))
+        S, J = omega.shape
+        a = _f64(np.atleast_2d(a), (S, J), "a")
+        b = _f64(np.atleast_2d(b), (S, J), "b")
+        amp = _f64(np.atleast_1d(amp), (S,), "amp")
+        bkg = _f64(np.atleast_1d(bkg), (S,), "bkg")
+        delays = _f64(np.atleast_1d(delays)).ravel()
+        G = delays.size
+        if out is None:
+            out = np.empty((G, S), dtype=np.float64)
+        elif out.shape != (G, S) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (G, S)")
+        _check(self._lib, self._lib.ipn_loglik_delay_grid(
+            self._h, T, _ptr(time), _ptr(exposure), _ptr(counts), S, J, _ptr(omega), _ptr(a), _ptr(b), _ptr(amp),
+            _ptr(bkg), G, _ptr(delays), _ptr(out)))
+        return out
+
+    def loglik_sky_grid(self, nbins, time, exposure, counts, sc_pos, ghat, omega, a, b, amp, bkg):
+        time = np.atleast_2d(_f64(time))
+        D, Tmax = time.shape
+        exposure = _f64(np.atleast_2d(exposure), (D, Tmax), "exposure")
+        counts = np.ascontiguousarray(np.atleast_2d(counts), dtype=np.int64)
+        if counts.shape != (D, Tmax):
+            raise ValueError(f"counts: expected shape {(D, Tmax)}, got {counts.shape}")
+        nbins = np.ascontiguousarray(nbins, dtype=np.int64)
+        if nbins.shape != (D,):
+            raise ValueError(f"nbins: expected shape {(D,)}, got {nbins.shape}")
+        sc_pos = _f64(sc_pos, (D, 3), "sc_pos")
+        ghat = np.atleast_2d(_f64(ghat))
+        if ghat.shape[1] != 3:
+            raise ValueError("ghat must be (P, 3)")
+        P = ghat.shape[0]
+        omega = np.atleast_2d(_f64(omega))
+        S, J = omega.shape
+        a = _f64(np.atleast_2d(a), (S, J), "a")
+        b = _f64(np.atleast_2d(b), (S, J), "b")
+        amp = _f64(np.atleast_2d(amp), (D, S), "amp")
+        bkg = _f64(np.atleast_2d(bkg), (D, S), "bkg")
+        out = np.empty((P, S), dtype=np.float64)
+        _check(self._lib, self._lib.ipn_loglik_sky_grid(
+            self._h, D, _ptr(nbins), Tmax, _ptr(time), _ptr(exposure), _ptr(counts), _ptr(sc_pos), P, _ptr(ghat), S, J,
+            _ptr(omega), _ptr(a), _ptr(b), _ptr(amp), _ptr(bkg), _ptr(out)))
+        return out
+
+    def poisson_counts(self, exposure, rates, bkg, seed):
+        rates = np.atleast_2d(_f64(rates))
+        S, T = rates.shape
+        exposure = _f64(exposure, (T,), "exposure")
+        bkg = _f64(np.atleast_1d(bkg), (S,), "bkg")
+        out = np.empty((S, T), dtype=np.int64)
+        _check(self._lib, self._lib.ipn_poisson_counts(self._h, T, _ptr(exposure), S, _ptr(rates), _ptr(bkg),
+                                                        C.c_uint64(int(seed) & (2**64 - 1)), _ptr(out)))
+        return out
+
+    # ---- device-pointer entry points (ints = CUdeviceptr, e.g. torch.Tensor.data_ptr()) -------------------
+    def rff_eval_dev(self, T, d_time, S, J, d_omega, d_a, d_b, d_shift, d_amp, d_out):
+        _check(self._lib, self._lib.ipn_rff_eval_dev(self._h, T, _p(d_time), S, J, _p(d_omega), _p(d_a), _p(d_b),
+                                                      _p(d_shift), _p(d_amp), _p(d_out)))
+
+    def loglik_delay_grid_dev(self, T, d_time, d_exposure, d_counts, S, J, d_omega, d_a, d_b, d_amp, d_bkg, G,
+                              d_delays, d_ll):
+        _check(self._lib, self._lib.ipn_loglik_delay_grid_dev(
+            self._h, T, _p(d_time), _p(d_exposure), _p(d_counts), S, J, _p(d_omega), _p(d_a), _p(d_b), _p(d_amp),
+            _p(d_bkg), G, _p(d_delays), _p(d_ll)))
+
+    def poisson_counts_dev(self, T, d_exposure, S, d_rates, d_bkg, seed, d_out):
+        _check(self._lib, self._lib.ipn_poisson_counts_dev(self._h, T, _p(d_exposure), S, _p(d_rates), _p(d_bkg),
+                                                            C.c_uint64(int(seed) & (2**64 - 1)), _p(d_out)))
+
+
+_default_ctx = {}
+_ctx_lock = threading.Lock()
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device (LOCAL_RANK selects the device under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _ctx_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+        return ctx

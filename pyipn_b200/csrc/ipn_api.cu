@@ -1,0 +1,422 @@
+// C ABI of libipn_b200 (include/ipn.h): context management, argument validation, host<->device staging.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ipn_common.cuh"
+
+namespace ipn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int Scratch::ensure(size_t bytes) {
+    if (bytes <= cap) return IPN_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return IPN_ERR_ALLOC;
+    }
+    cap = want;
+    return IPN_OK;
+}
+
+void Scratch::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int ctx_guard(ipn_ctx* ctx) {
+    if (!ctx) {
+        set_error("ipn_ctx is NULL");
+        return IPN_ERR_INVALID_ARGUMENT;
+    }
+    IPN_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return IPN_OK;
+}
+
+static int begin_timing(ipn_ctx* ctx) {
+    IPN_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return IPN_OK;
+}
+static int end_timing(ipn_ctx* ctx) {
+    IPN_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return IPN_OK;
+}
+static int finish_timing(ipn_ctx* ctx) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
+        ctx->last_kernel_ms = ms;
+    else
+        cudaGetLastError();
+    return IPN_OK;
+}
+
+static int h2d(ipn_ctx* ctx, Scratch& sc, const void* host, size_t bytes) {
+    int rc = sc.ensure(bytes ? bytes : 8);
+    if (rc) return rc;
+    if (bytes) IPN_CUDA_CHECK(cudaMemcpyAsync(sc.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return IPN_OK;
+}
+
+static bool all_finite(const double* v, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        if (!isfinite(v[i])) return false;
+    return true;
+}
+
+}  // namespace ipn
+
+using namespace ipn;
+
+extern "C" {
+
+const char* ipn_last_error(void) { return g_err; }
+const char* ipn_version(void) { return "libipn_b200 0.1 (sm_100a)"; }
+
+int ipn_ctx_create(int device, ipn_ctx** out) {
+    if (!out) {
+        set_error("out is NULL");
+        return IPN_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libipn_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return IPN_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (0..%d)", device, n - 1);
+        return IPN_ERR_INVALID_ARGUMENT;
+    }
+    cudaDeviceProp prop;
+    IPN_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libipn_b200 only contains sm_100a code (B200)", device, prop.major, prop.minor);
+        return IPN_ERR_NO_DEVICE;
+    }
+    IPN_CUDA_CHECK(cudaSetDevice(device));
+    ipn_ctx* ctx = new ipn_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return IPN_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return IPN_OK;
+}
+
+void ipn_ctx_destroy(ipn_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->wtab.release();
+    ctx->binprep.release();
+    ctx->draws.release();
+    ctx->accum.release();
+    ctx->misc.release();
+    for (auto& s : ctx->io) s.release();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int ipn_ctx_set_stream(ipn_ctx* ctx, void* cuda_stream) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return IPN_OK;
+}
+
+int ipn_ctx_synchronize(ipn_ctx* ctx) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
+int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
+    if (!ctx) {
+        set_error("ipn_ctx is NULL");
+        return IPN_ERR_INVALID_ARGUMENT;
+    }
+    switch (key) {
+        case IPN_OPT_LOGLIK_IMPL:
+            IPN_REQUIRE(value >= 0 && value <= 2, "IPN_OPT_LOGLIK_IMPL must be 0, 1 or 2");
+            ctx->loglik_impl = (int)value;
+            return IPN_OK;
+        case IPN_OPT_PRECISE_W:
+            ctx->precise_w = value != 0;
+            return IPN_OK;
+        case IPN_OPT_DRAW_BATCH:
+            IPN_REQUIRE(value >= 0, "IPN_OPT_DRAW_BATCH must be >= 0");
+            ctx->draw_batch = value;
+            return IPN_OK;
+        default:
+            set_error("unknown option key %d", key);
+            return IPN_ERR_INVALID_ARGUMENT;
+    }
+}
+
+uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+
+// ---------------------------------------------------------------------------------------------------
+static int check_rff_args(int64_t T, const void* time, int64_t S, int64_t J, const void* omega, const void* a,
+                          const void* b, const void* shift, const void* amp, const void* out) {
+    IPN_REQUIRE(T >= 0 && S >= 0 && J >= 1, "need T >= 0, S >= 0, J >= 1 (got T=%lld S=%lld J=%lld)", (long long)T,
+                (long long)S, (long long)J);
+    if (J > IPN_MAX_J) {
+        set_error("J = %lld exceeds IPN_MAX_J = %d", (long long)J, IPN_MAX_J);
+        return IPN_ERR_UNSUPPORTED;
+    }
+    if (T == 0 || S == 0) return IPN_OK;
+    IPN_REQUIRE(time && omega && a && b && shift && amp && out, "NULL array argument");
+    return IPN_OK;
+}
+
+int ipn_rff_eval_dev(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
+                     const double* a, const double* b, const double* shift, const double* amp, double* out) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    rc = check_rff_args(T, time, S, J, omega, a, b, shift, amp, out);
+    if (rc) return rc;
+    if (T == 0 || S == 0) return IPN_OK;
+    begin_timing(ctx);
+    rc = launch_rff_eval(ctx, T, time, S, J, omega, a, b, shift, amp, out);
+    end_timing(ctx);
+    return rc;
+}
+
+int ipn_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
+                 const double* a, const double* b, const double* shift, const double* amp, double* out) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    rc = check_rff_args(T, time, S, J, omega, a, b, shift, amp, out);
+    if (rc) return rc;
+    if (T == 0 || S == 0) return IPN_OK;
+    const size_t sj = (size_t)S * J * sizeof(double);
+    if ((rc = h2d(ctx, ctx->io[0], time, (size_t)T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[1], omega, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[2], a, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[3], b, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[4], shift, (size_t)S * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[5], amp, (size_t)S * 8))) return rc;
+    if ((rc = ctx->io[6].ensure((size_t)S * T * 8))) return rc;
+    begin_timing(ctx);
+    rc = launch_rff_eval(ctx, T, ctx->io[0].as<double>(), S, J, ctx->io[1].as<double>(), ctx->io[2].as<double>(),
+                         ctx->io[3].as<double>(), ctx->io[4].as<double>(), ctx->io[5].as<double>(),
+                         ctx->io[6].as<double>());
+    end_timing(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaMemcpyAsync(out, ctx->io[6].p, (size_t)S * T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int check_grid_shapes(int64_t T, int64_t S, int64_t J, int64_t G) {
+    IPN_REQUIRE(T >= 0 && S >= 0 && G >= 0 && J >= 1, "need T, S, G >= 0 and J >= 1 (got T=%lld S=%lld J=%lld G=%lld)",
+                (long long)T, (long long)S, (long long)J, (long long)G);
+    if (J > IPN_MAX_J) {
+        set_error("J = %lld exceeds IPN_MAX_J = %d", (long long)J, IPN_MAX_J);
+        return IPN_ERR_UNSUPPORTED;
+    }
+    return IPN_OK;
+}
+
+static int check_grid_host_values(int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                                  int64_t S, int64_t J, const double* omega, const double* a, const double* b,
+                                  const double* amp, const double* bkg) {
+    IPN_REQUIRE(all_finite(time, T), "time contains a non-finite value");
+    for (int64_t i = 0; i < T; ++i) {
+        IPN_REQUIRE(counts[i] >= 0, "counts[%lld] = %lld is negative", (long long)i, (long long)counts[i]);
+        IPN_REQUIRE(isfinite(exposure[i]) && exposure[i] >= 0.0, "exposure[%lld] is negative or non-finite", (long long)i);
+    }
+    IPN_REQUIRE(all_finite(omega, S * J) && all_finite(a, S * J) && all_finite(b, S * J),
+                "omega/a/b contain a non-finite value");
+    for (int64_t s = 0; s < S; ++s) {
+        IPN_REQUIRE(isfinite(bkg[s]) && bkg[s] > 0.0, "bkg[%lld] must be finite and > 0", (long long)s);
+        IPN_REQUIRE(isfinite(amp[s]) && amp[s] >= 0.0, "amp[%lld] must be finite and >= 0", (long long)s);
+        IPN_REQUIRE(amp[s] == 0.0 || fabs(log2(amp[s] / bkg[s])) < 100.0, "amp/bkg ratio of draw %lld out of range",
+                    (long long)s);
+    }
+    return IPN_OK;
+}
+
+int ipn_loglik_delay_grid_dev(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure,
+                              const int64_t* counts, int64_t S, int64_t J, const double* omega, const double* a,
+                              const double* b, const double* amp, const double* bkg, int64_t G, const double* delays,
+                              double* ll) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    rc = check_grid_shapes(T, S, J, G);
+    if (rc) return rc;
+    if (S == 0 || G == 0) return IPN_OK;
+    IPN_REQUIRE(omega && a && b && amp && bkg && delays && ll && (T == 0 || (time && exposure && counts)),
+                "NULL array argument");
+    begin_timing(ctx);
+    rc = run_loglik_grid(ctx, T, time, exposure, counts, S, J, omega, a, b, amp, bkg, G, delays, ll, false);
+    end_timing(ctx);
+    return rc;
+}
+
+int ipn_loglik_delay_grid(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                          int64_t S, int64_t J, const double* omega, const double* a, const double* b,
+                          const double* amp, const double* bkg, int64_t G, const double* delays, double* ll) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    rc = check_grid_shapes(T, S, J, G);
+    if (rc) return rc;
+    if (S == 0 || G == 0) return IPN_OK;
+    IPN_REQUIRE(omega && a && b && amp && bkg && delays && ll && (T == 0 || (time && exposure && counts)),
+                "NULL array argument");
+    rc = check_grid_host_values(T, time, exposure, counts, S, J, omega, a, b, amp, bkg);
+    if (rc) return rc;
+    IPN_REQUIRE(all_finite(delays, G), "delays contain a non-finite value");
+    const size_t sj = (size_t)S * J * 8;
+    if ((rc = h2d(ctx, ctx->io[0], time, (size_t)T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[1], exposure, (size_t)T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[2], counts, (size_t)T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[3], omega, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[4], a, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[5], b, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[6], amp, (size_t)S * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[7], bkg, (size_t)S * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[8], delays, (size_t)G * 8))) return rc;
+    if ((rc = ctx->io[9].ensure((size_t)G * S * 8))) return rc;
+    begin_timing(ctx);
+    rc = run_loglik_grid(ctx, T, ctx->io[0].as<double>(), ctx->io[1].as<double>(), ctx->io[2].as<int64_t>(), S, J,
+                         ctx->io[3].as<double>(), ctx->io[4].as<double>(), ctx->io[5].as<double>(),
+                         ctx->io[6].as<double>(), ctx->io[7].as<double>(), G, ctx->io[8].as<double>(),
+                         ctx->io[9].as<double>(), false);
+    end_timing(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaMemcpyAsync(ll, ctx->io[9].p, (size_t)G * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
+int ipn_loglik_sky_grid(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t Tmax, const double* time,
+                        const double* exposure, const int64_t* counts, const double* sc_pos, int64_t P,
+                        const double* ghat, int64_t S, int64_t J, const double* omega, const double* a,
+                        const double* b, const double* amp, const double* bkg, double* ll) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(D >= 1 && Tmax >= 0, "need D >= 1 and Tmax >= 0");
+    rc = check_grid_shapes(Tmax, S, J, P);
+    if (rc) return rc;
+    if (S == 0 || P == 0) return IPN_OK;
+    IPN_REQUIRE(nbins && sc_pos && ghat && omega && a && b && amp && bkg && ll && (Tmax == 0 || (time && exposure && counts)),
+                "NULL array argument");
+    IPN_REQUIRE(all_finite(sc_pos, D * 3) && all_finite(ghat, P * 3), "sc_pos / ghat contain a non-finite value");
+    for (int64_t d = 0; d < D; ++d) {
+        IPN_REQUIRE(nbins[d] >= 0 && nbins[d] <= Tmax, "nbins[%lld] = %lld outside 0..Tmax", (long long)d, (long long)nbins[d]);
+        rc = check_grid_host_values(nbins[d], time + d * Tmax, exposure + d * Tmax, counts + d * Tmax, S, J, omega, a, b,
+                                    amp + d * S, bkg + d * S);
+        if (rc) return rc;
+    }
+    const size_t sj = (size_t)S * J * 8, dt = (size_t)D * Tmax * 8;
+    if ((rc = h2d(ctx, ctx->io[0], time, dt))) return rc;
+    if ((rc = h2d(ctx, ctx->io[1], exposure, dt))) return rc;
+    if ((rc = h2d(ctx, ctx->io[2], counts, dt))) return rc;
+    if ((rc = h2d(ctx, ctx->io[3], omega, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[4], a, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[5], b, sj))) return rc;
+    if ((rc = h2d(ctx, ctx->io[6], amp, (size_t)D * S * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[7], bkg, (size_t)D * S * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[8], sc_pos, (size_t)D * 3 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[10], ghat, (size_t)P * 3 * 8))) return rc;
+    if ((rc = ctx->io[9].ensure((size_t)P * S * 8))) return rc;
+    if ((rc = ctx->io[11].ensure((size_t)D * P * 8))) return rc;
+    begin_timing(ctx);
+    rc = launch_sky_delays(ctx, D, ctx->io[8].as<double>(), P, ctx->io[10].as<double>(), ctx->io[11].as<double>());
+    if (rc) return rc;
+    bool first = true;
+    for (int64_t d = 0; d < D; ++d) {
+        // detector 0 is unshifted (rff_omega_ipn.stan:144): its delay column is identically zero, so a 1-point
+        // grid would do; it is kept on the common path (its cost is 1/D of the call) to share one code path.
+        rc = run_loglik_grid(ctx, nbins[d], ctx->io[0].as<double>() + d * Tmax, ctx->io[1].as<double>() + d * Tmax,
+                             ctx->io[2].as<int64_t>() + d * Tmax, S, J, ctx->io[3].as<double>(), ctx->io[4].as<double>(),
+                             ctx->io[5].as<double>(), ctx->io[6].as<double>() + d * S, ctx->io[7].as<double>() + d * S, P,
+                             ctx->io[11].as<double>() + d * P, ctx->io[9].as<double>(), !first);
+        if (rc) return rc;
+        first = false;
+    }
+    end_timing(ctx);
+    IPN_CUDA_CHECK(cudaMemcpyAsync(ll, ctx->io[9].p, (size_t)P * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int ipn_poisson_counts_dev(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t S, const double* rates,
+                           const double* bkg, uint64_t seed, int64_t* out) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(T >= 0 && S >= 0, "need T >= 0 and S >= 0");
+    if (T == 0 || S == 0) return IPN_OK;
+    IPN_REQUIRE(exposure && rates && bkg && out, "NULL array argument");
+    begin_timing(ctx);
+    rc = launch_poisson_counts(ctx, T, exposure, S, rates, bkg, seed, out);
+    end_timing(ctx);
+    return rc;
+}
+
+int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t S, const double* rates,
+                       const double* bkg, uint64_t seed, int64_t* out) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(T >= 0 && S >= 0, "need T >= 0 and S >= 0");
+    if (T == 0 || S == 0) return IPN_OK;
+    IPN_REQUIRE(exposure && rates && bkg && out, "NULL array argument");
+    if ((rc = h2d(ctx, ctx->io[0], exposure, (size_t)T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[1], rates, (size_t)S * T * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[2], bkg, (size_t)S * 8))) return rc;
+    if ((rc = ctx->io[3].ensure((size_t)S * T * 8))) return rc;
+    begin_timing(ctx);
+    rc = launch_poisson_counts(ctx, T, ctx->io[0].as<double>(), S, ctx->io[1].as<double>(), ctx->io[2].as<double>(), seed,
+                               ctx->io[3].as<int64_t>());
+    end_timing(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaMemcpyAsync(out, ctx->io[3].p, (size_t)S * T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
+int ipn_microbench(ipn_ctx* ctx, int which, double* result) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(result != nullptr, "result is NULL");
+    return run_microbench(ctx, which, result);
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Shared internals of libipn_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/ipn.h"
+
+namespace ipn {
+
+void set_error(const char* fmt, ...);
+
+#define IPN_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ipn::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return IPN_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define IPN_REQUIRE(cond, ...)              \
+    do {                                    \
+        if (!(cond)) {                      \
+            ipn::set_error(__VA_ARGS__);    \
+            return IPN_ERR_INVALID_ARGUMENT; \
+        }                                   \
+    } while (0)
+
+// growable device scratch buffer owned by the context
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace ipn
+
+struct ipn_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    double last_kernel_ms = 0.0;
+    // options
+    int loglik_impl = 0;
+    int precise_w = 1;
+    int64_t draw_batch = 0;
+    // scratch
+    ipn::Scratch wtab;     // delay tables of the current draw batch
+    ipn::Scratch binprep;  // per-call per-bin constants
+    ipn::Scratch draws;    // per-draw constants
+    ipn::Scratch accum;    // per-(grid point) accumulators
+    ipn::Scratch io[12];   // staging for the host-pointer entry points
+    ipn::Scratch misc;
+    void* pinned = nullptr;  // pinned host bounce buffer
+    size_t pinned_cap = 0;
+};
+
+namespace ipn {
+
+// ---- kernels' host launchers (each returns IPN_OK / error, bumps ctx->launches) -----------------------
+int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
+                    const double* a, const double* b, const double* shift, const double* amp, double* out);
+
+// Accumulates into d_ll (G x S, must be zeroed or hold a previous detector's sum when accumulate = true).
+int run_loglik_grid(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                    int64_t S, int64_t J, const double* omega, const double* a, const double* b, const double* amp,
+                    const double* bkg, int64_t G, const double* delays, double* ll, bool accumulate);
+
+int launch_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t S, const double* rates,
+                          const double* bkg, uint64_t seed, int64_t* out);
+
+int launch_sky_delays(ipn_ctx* ctx, int64_t D, const double* sc_pos, int64_t P, const double* ghat, double* delays);
+
+int run_microbench(ipn_ctx* ctx, int which, double* result);
+
+}  // namespace ipn

@@ -1,0 +1,91 @@
+// Pieces shared by the FP32-pipe and the tcgen05 delay-grid log-likelihood kernels.
+//
+// Arithmetic restated from pyipn/stan_models/functions.stan:23-35 (see DESIGN.md "Likelihood algebra"):
+//   mu_i = e_i (A f_i + B) = e_i B (1 + u_i),  u_i = (A/B) f(t_i - Delta) = 2^(x_i),
+//   x_i  = log2(A/B) + log2(e) * sum_j [a_j cos(w_j (t_i - Delta)) + b_j sin(w_j (t_i - Delta))]
+//        = c_s + sum_k Phi[i,k] W[k,g]                     (angle addition; Phi depends on bin, W on delay)
+//   ll   = C_s + ln2 * R,   R = sum_i [ n_i log2(1 + u_i) - kappa_i u_i ],  kappa_i = e_i B / ln2
+//   C_s  = sum_i [ n_i log(e_i) ] + N log B - B sum_i e_i - sum_i lgamma(n_i + 1)          (fp64, once per draw)
+// Every constant factor that multiplies a sum over ~1e5 bins is applied in fp64 (or as an fp32 hi/lo pair):
+// a single fp32 rounding of such a factor is a 6e-8 relative bias on a sum of ~5e4 nats, i.e. > 1e-3 nats.
+#pragma once
+#include "ipn_common.cuh"
+
+namespace ipn {
+
+constexpr double kLog2e = 1.4426950408889634074;
+constexpr double kLn2 = 0.69314718055994530942;
+
+// per-call bin constants: [0] = sum n, [1] = sum n log e, [2] = sum e, [3] = sum lgamma(n+1)
+struct DrawConst {
+    double C;      // additive constant of the draw (natural log units)
+    double kap;    // B / ln2
+    float c_hi;    // log2(A/B) split in two fp32
+    float c_lo;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u,  u = 2^x.
+__device__ __forceinline__ float poisson_term(float x, float n, float khi, float klo) {
+    const float u = ex2_approx(x);
+    // log2(1 + u): MUFU for u >= 2^-12, cubic series below (1 + u would round away most of u there)
+    const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
+    const float lg = (u < 2.44140625e-4f) ? series : lg2_approx(1.0f + u);
+    const float ku = fmaf(khi, u, klo * u);
+    return fmaf(n, lg, -ku);
+}
+
+// sin and cos of r (|r| <= pi + eps) given as fp32 hi + lo; see rff_eval.cu for the derivation of the constants.
+__device__ __forceinline__ void sincos_reduced_f32(float rh, float rl, float& s, float& c) {
+    const float qf = rintf(rh * 0.636619772367581343f);
+    const int q = (int)qf;
+    float y = fmaf(qf, -1.57079637050628662109375f, rh);
+    y = fmaf(qf, 4.37113900018624283e-8f, y);
+    y += rl;
+    const float y2 = y * y;
+    float ps = fmaf(y2, 2.7237618209228658e-06f, -0.00019839989971813914f);
+    ps = fmaf(ps, y2, 0.008333331692152657f);
+    ps = fmaf(ps, y2, -0.16666666663377125f);
+    const float sy = fmaf(ps * y2, y, y);
+    float pc = fmaf(y2, -2.7290681690617153e-07f, 2.4800519567960354e-05f);
+    pc = fmaf(pc, y2, -0.0013888887519541376f);
+    pc = fmaf(pc, y2, 0.04166666666392175f);
+    const float cy = fmaf(fmaf(pc, y2, -0.5f), y2, 1.0f);
+    const float ss = (q & 1) ? cy : sy;
+    const float cc = (q & 1) ? sy : cy;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// fp64 phase -> (sin, cos) in fp32 with ~2e-8 rms error regardless of |phase| (< 2^40 or so).
+__device__ __forceinline__ void sincos_phase(double ph, float& s, float& c) {
+    const double kq = rint(ph * 0.15915494309189534561);
+    double r = fma(kq, -6.283185307179586232, ph);
+    r = fma(kq, -2.4492935982947064e-16, r);
+    const float rh = (float)r;
+    const float rl = (float)(r - (double)rh);
+    sincos_reduced_f32(rh, rl, s, c);
+}
+
+int prepare_bin_constants(ipn_ctx* ctx, int64_t T, const double* exposure, const int64_t* counts, double* d_binc);
+int prepare_draw_constants(ipn_ctx* ctx, int64_t S, const double* amp, const double* bkg, const double* d_binc,
+                           DrawConst* d_dc);
+int finalize_loglik(ipn_ctx* ctx, int64_t S0, int64_t Sb, int64_t S, int64_t G, int64_t Gpad, const double* d_R,
+                    const DrawConst* d_dc, double* d_ll, bool accumulate);
+
+// FP32-pipe implementation (loglik_simt.cu)
+int run_loglik_grid_simt(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                         int64_t S, int64_t J, const double* omega, const double* a, const double* b,
+                         const DrawConst* d_dc, int64_t G, const double* delays, double* ll, bool accumulate);
+
+}  // namespace ipn

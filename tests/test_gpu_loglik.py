@@ -1,0 +1,163 @@
+"""GPU parity: delay-grid / sky-grid Poisson log-likelihood vs the float64 oracle composition.
+
+Tolerances (BASELINE.json north_star): absolute 1e-3 nats on log-likelihood sums, argmax indices exact."""
+import numpy as np
+import pytest
+
+from oracle import ipn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-3
+
+
+def _fold_golden(g):
+    w, a, b = zip(*[orc.fold_params(g["omega1"][:, s], g["omega2"][:, s], g["beta1"][:, s], g["beta2"][:, s], 1.0,
+                                    g["scale"][0, s], g["scale"][1, s]) for s in range(g["omega1"].shape[1])])
+    return np.array(w), np.array(a), np.array(b)
+
+
+@pytest.mark.parametrize("precise", [1, 0])
+def test_delay_grid_reference_golden(ctx, loglik_golden, precise):
+    from pyipn_b200._lib import OPT_PRECISE_W
+
+    g = loglik_golden
+    w, a, b = _fold_golden(g)
+    ctx.set_option(OPT_PRECISE_W, precise)
+    try:
+        ll = ctx.loglik_delay_grid(g["time"], g["exposure"], g["counts"], w, a, b, g["amp"], g["bkg"], g["delays"])
+    finally:
+        ctx.set_option(OPT_PRECISE_W, 1)
+    assert ll.shape == g["ll"].shape
+    assert np.abs(ll - g["ll"]).max() < ATOL
+    np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(g["ll"], axis=0))
+
+
+def test_facade_fit_delay_grid(ctx, loglik_golden):
+    from pyipn_b200 import Fit
+
+    g = loglik_golden
+    fit = Fit(beta1=g["beta1"], beta2=g["beta2"], omega=np.stack([g["omega1"], g["omega2"]]), scale=g["scale"],
+              background=np.stack([g["bkg"], g["bkg"]]), amplitude=g["amp"][None, :], dt=np.zeros((1, 3)))
+    ll = fit.delay_grid_loglik(1, g["time"], g["exposure"], g["counts"], g["delays"])
+    assert np.abs(ll - g["ll"]).max() < ATOL
+
+
+@pytest.mark.parametrize("T,G,S,k", [(1, 1, 1, 1), (63, 5, 2, 3), (64, 128, 1, 50), (65, 129, 3, 50), (1000, 300, 5, 50),
+                                     (20_000, 64, 2, 50)])
+def test_delay_grid_vs_oracle_ragged_shapes(ctx, T, G, S, k):
+    rng = np.random.default_rng(T * 7 + G + S)
+    edges = np.cumsum(rng.uniform(0.002, 0.01, T + 1))
+    time = 0.5 * (edges[1:] + edges[:-1])
+    expo = np.diff(edges)
+    omega = rng.normal(size=(S, 2 * k)) * np.where(np.arange(2 * k) < k, 0.05, 2.0)
+    a = rng.normal(size=(S, 2 * k)) * 0.12
+    b = rng.normal(size=(S, 2 * k)) * 0.12
+    amp = np.exp(rng.normal(5.0, 0.3, S))
+    bkg = np.exp(rng.normal(np.log(500.0), 0.1, S))
+    f = np.exp(orc.log_intensity_folded(time - 0.05, omega[0], a[0], b[0]))
+    counts = rng.poisson(expo * (amp[0] * f + bkg[0])).astype(np.int64)
+    delays = np.sort(rng.uniform(-0.5, 0.5, G))
+    ll = ctx.loglik_delay_grid(time, expo, counts, omega, a, b, amp, bkg, delays)
+    exp = orc.loglik_delay_grid(counts, time, expo, omega, a, b, amp, bkg, delays)
+    assert np.abs(ll - exp).max() < ATOL
+    if G > 1:
+        np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(exp, axis=0))
+
+
+def test_delay_grid_edge_cases(ctx):
+    rng = np.random.default_rng(2)
+    T = 300
+    time = np.arange(T) * 0.01
+    expo = np.full(T, 0.01)
+    omega = rng.normal(size=(2, 20))
+    a = rng.normal(size=(2, 20)) * 0.2
+    b = rng.normal(size=(2, 20)) * 0.2
+    delays = np.linspace(-0.2, 0.2, 7)
+    # all-zero counts; amplitude 0 in draw 1 (background only); tiny source in draw 0
+    counts = np.zeros(T, dtype=np.int64)
+    amp = np.array([1e-6, 0.0])
+    bkg = np.array([500.0, 3.0])
+    ll = ctx.loglik_delay_grid(time, expo, counts, omega, a, b, amp, bkg, delays)
+    exp = orc.loglik_delay_grid(counts, time, expo, omega, a, b, amp, bkg, delays)
+    assert np.abs(ll - exp).max() < 1e-6
+    # bright source, large counts (lgamma term matters), zero-exposure bins with zero counts
+    amp = np.array([5e4, 2e3])
+    f = np.exp(orc.log_intensity_folded(time, omega[0], a[0], b[0]))
+    counts = rng.poisson(expo * (amp[0] * f + bkg[0])).astype(np.int64)
+    expo2 = expo.copy()
+    expo2[10:20] = 0.0
+    counts[10:20] = 0
+    ll = ctx.loglik_delay_grid(time, expo2, counts, omega, a, b, amp, bkg, delays)
+    exp = orc.loglik_delay_grid(counts, time, expo2, omega, a, b, amp, bkg, delays)
+    assert np.abs(ll - exp).max() < ATOL
+    # empty grids / empty bins
+    assert ctx.loglik_delay_grid(time, expo, counts, omega, a, b, amp, bkg, np.zeros(0)).shape == (0, 2)
+    ll0 = ctx.loglik_delay_grid(np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int64), omega, a, b, amp, bkg, delays)
+    np.testing.assert_array_equal(ll0, 0.0)
+
+
+def test_delay_grid_rejects_bad_input(ctx):
+    from pyipn_b200 import IpnError
+
+    t = np.arange(10.0)
+    e = np.ones(10)
+    n = np.ones(10, dtype=np.int64)
+    w = np.ones((1, 4))
+    with pytest.raises(IpnError):
+        ctx.loglik_delay_grid(t, e, n, w, w, w, [1.0], [0.0], [0.0])  # bkg must be > 0
+    with pytest.raises(IpnError):
+        ctx.loglik_delay_grid(t, e, -n, w, w, w, [1.0], [1.0], [0.0])  # negative counts
+    with pytest.raises(IpnError):
+        ctx.loglik_delay_grid(t, e, n, w * np.nan, w, w, [1.0], [1.0], [0.0])
+
+
+def test_config2_full_size_subsample_and_argmax(ctx):
+    """BASELINE config 2 at full size (4096 delays x 1e5 bins, K=50, one draw): oracle on a 48-delay subsample
+    (incl. the neighbourhood of the maximum), exact argmax, and the reported best-vs-second gap."""
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=100_000, G=4096, S=1)
+    ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    best = int(np.argmax(ll[:, 0]))
+    assert abs(w["delays"][best] - w["true_delay"]) < 2.0 / 4096 + 2e-3
+    idx = np.unique(np.concatenate([np.arange(0, 4096, 128), np.arange(best - 8, best + 8)]).clip(0, 4095))
+    exp = orc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"],
+                                w["delays"][idx])
+    err = np.abs(ll[idx, 0] - exp[:, 0]).max()
+    assert err < ATOL, err
+    assert idx[np.argmax(exp[:, 0])] == best
+    srt = np.sort(ll[:, 0])
+    assert srt[-1] - srt[-2] > 10 * err  # the argmax is decided by physics, not by rounding
+
+
+def test_linearity_in_counts_full_size(ctx):
+    """Size-independent property: the Poisson sum is linear in the counts vector apart from the lgamma term:
+    ll(n1 + n2) + ll(0) - ll(n1) - ll(n2) = -sum[lgamma(n1+n2+1) - lgamma(n1+1) - lgamma(n2+1)] for every grid point."""
+    from scipy.special import gammaln
+
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=100_000, G=256, S=2)
+    rng = np.random.default_rng(0)
+    n1 = w["counts"]
+    n2 = rng.poisson(0.7, size=n1.shape).astype(np.int64)
+    args = (w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    f = lambda n: ctx.loglik_delay_grid(w["time"], w["exposure"], n, *args)
+    lhs = f(n1 + n2) + f(np.zeros_like(n1)) - f(n1) - f(n2)
+    rhs = -(gammaln(n1 + n2 + 1.0) - gammaln(n1 + 1.0) - gammaln(n2 + 1.0)).sum()
+    assert np.abs(lhs - rhs).max() < 4 * ATOL
+
+
+def test_sky_grid_vs_oracle(ctx):
+    from pyipn_b200.synth import sky_grid_workload
+
+    w = sky_grid_workload(D=3, T=1500, S=2, nside=2, dt_bin=0.01)
+    # ragged detectors: detector 2 has fewer valid bins (padding must be ignored)
+    w["nbins"][2] = 1200
+    ll = ctx.loglik_sky_grid(w["nbins"], w["time"], w["exposure"], w["counts"], w["sc_pos"], w["ghat"], w["omega"], w["a"],
+                             w["b"], w["amp"], w["bkg"])
+    exp = orc.loglik_sky_grid(w["counts"], w["time"], w["exposure"], w["nbins"], w["sc_pos"], w["ghat"], w["omega"], w["a"],
+                              w["b"], w["amp"], w["bkg"])
+    assert ll.shape == (48, 2)
+    assert np.abs(ll - exp).max() < ATOL
+    np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(exp, axis=0))

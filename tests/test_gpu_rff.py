@@ -1,0 +1,79 @@
+"""GPU parity: ipn_rff_eval (through the C ABI and the reference-named Python facade) vs the reference fixtures / oracle.
+
+Tolerance (BASELINE.json north_star): relative 1e-6 on lambda."""
+import numpy as np
+import pytest
+
+from oracle import ipn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def test_rff_golden_single_and_multiscale(ctx, rff_golden):
+    from pyipn_b200 import RFF, RFF_multiscale
+
+    g = rff_golden
+    got = RFF(g["A_time"], g["A_omega1"], g["A_omega2"], g["A_beta1"], g["A_beta2"], float(g["A_bw"]), g["A_scale"][1])
+    np.testing.assert_allclose(got, g["A_rff"], rtol=RTOL)
+    got = RFF_multiscale(g["A_time"], g["A_omega1"], g["A_omega2"], g["A_beta1"], g["A_beta2"], float(g["A_bw"]),
+                         g["A_scale"][0], g["A_scale"][1])
+    np.testing.assert_allclose(got, g["A_rff_ms"], rtol=RTOL)
+    assert got.dtype == np.float64 and got.shape == g["A_time"].shape
+
+
+def test_expected_rate_golden_strided_draws(ctx, rff_golden):
+    from pyipn_b200 import _expeced_rate, _expeced_rate_multiscale
+
+    g = rff_golden
+    args = (g["B_time"], g["B_omega1"], g["B_omega2"], g["B_beta1"], g["B_beta2"], g["B_bw"])
+    np.testing.assert_allclose(_expeced_rate(*args, g["B_scale"][1], g["B_amp"], g["B_dt"], 7), g["B_rate_single"], rtol=RTOL)
+    np.testing.assert_allclose(_expeced_rate_multiscale(*args, g["B_scale"], g["B_amp"], g["B_dt"], 7), g["B_rate_multi"],
+                               rtol=RTOL)
+
+
+def test_rff_edge_cases(ctx, rff_golden):
+    from pyipn_b200 import RFF, RFF_multiscale
+
+    g = rff_golden
+    got = RFF_multiscale(g["C_time"], g["C_omega1"], g["C_omega2"], g["C_beta1"], g["C_beta2"], 1.0, 0.4, 1.3)
+    np.testing.assert_allclose(got, g["C_rff_ms"], rtol=RTOL)  # one bin, k = 1, |phase| ~ 9e3 rad
+    np.testing.assert_array_equal(RFF(g["A_time"], np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3), 1.0, 1.0), 1.0)
+    assert RFF(np.zeros(0), np.ones(2), np.ones(2), np.ones(2), np.ones(2), 1.0, 1.0).shape == (0,)
+
+
+@pytest.mark.parametrize("T,S,k", [(1, 1, 1), (511, 3, 7), (513, 2, 50), (100_000, 4, 50), (2049, 64, 50)])
+def test_rff_eval_vs_oracle_shapes(ctx, T, S, k):
+    rng = np.random.default_rng(T + S + k)
+    time = np.sort(rng.uniform(-20.0, 120.0, T))
+    omega = rng.normal(size=(S, 2 * k)) * np.where(np.arange(2 * k) < k, 0.01, 1.0)
+    a = rng.normal(size=(S, 2 * k)) * 0.15
+    b = rng.normal(size=(S, 2 * k)) * 0.15
+    shift = rng.normal(0, 1.0, S)
+    amp = np.exp(rng.normal(size=S))
+    got = ctx.rff_eval(time, omega, a, b, shift, amp)
+    for s in range(S):
+        exp = amp[s] * np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s]))
+        np.testing.assert_allclose(got[s], exp, rtol=RTOL)
+
+
+def test_rff_eval_huge_phases(ctx):
+    """Sky-scale shifts (1e3 s) and large absolute times: phases ~1e5 rad must still meet 1e-6."""
+    rng = np.random.default_rng(9)
+    time = 5.0e4 + np.linspace(0, 100, 5000)
+    omega = rng.normal(size=(2, 100)) * 2.0
+    a = rng.normal(size=(2, 100)) * 0.1
+    b = rng.normal(size=(2, 100)) * 0.1
+    shift = np.array([-1.0e3, 777.7])
+    got = ctx.rff_eval(time, omega, a, b, shift, np.ones(2))
+    for s in range(2):
+        np.testing.assert_allclose(got[s], np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])), rtol=RTOL)
+
+
+def test_argument_errors(ctx):
+    from pyipn_b200 import IpnError
+
+    with pytest.raises(IpnError):
+        ctx.rff_eval(np.arange(4.0), np.ones((1, 600)), np.ones((1, 600)), np.ones((1, 600)), [0.0], [1.0])  # J > IPN_MAX_J
+    with pytest.raises(ValueError):
+        ctx.rff_eval(np.arange(4.0), np.ones((2, 4)), np.ones((1, 4)), np.ones((2, 4)), [0.0, 0.0], [1.0, 1.0])
