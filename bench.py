@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Headline benchmark: RFF Poisson log-likelihood grid, (grid-point x bin)/s.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on the host cores
+
+Workload (``config.workload``): BASELINE.json config 3 -- 4096 trial delays x posterior draws x 1e5 bins of 1 ms,
+K = 50 RFF features -- sharded by draws, ``--draws-per-gpu`` (default 500 = 4000/8) draws per rank, so N = 8 is
+the full 4096 x 4000 x 1e5 grid and the scaling is weak.  One step = one pass over the rank's shard (delay
+tables, contraction + fused Poisson reduction, finalisation) plus, for N > 1, the all-gather of the
+log-likelihood blocks.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_UNIT = 400.0  # 2J = 200 FP32 FMA per (grid-point x bin) in the contraction form
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--draws-per-gpu", type=int, default=500)
+    ap.add_argument("--delays", type=int, default=4096)
+    ap.add_argument("--bins", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--loglik-impl", type=int, default=0, help="0 auto, 1 FP32-pipe, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, world):
+    return (f"config3 posterior-predictive sweep shard: {a.delays} delays x {a.draws_per_gpu} draws/GPU x {a.bins} bins, "
+            f"K={a.k} (J={2 * a.k}); {world} rank(s) -> {a.draws_per_gpu * world} draws total")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (rank 0)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(self.samples))
+
+
+def run_reference(a, rank, world):
+    """The reference's CPU implementation of the path (oracle port; the reference itself is Python and cannot travel)."""
+    if rank != 0:
+        return
+    from oracle.cpu_bench import time_oracle
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, a.draws_per_gpu), k=a.k)
+    cores = os.cpu_count() or 1
+    vals, secs = [], []
+    for step in range(a.warmup + a.steps):
+        r = time_oracle(w, cores=cores)
+        if step >= a.warmup:
+            vals.append(r["value"])
+            secs.append(r["seconds"])
+    v = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": "RFF Poisson loglik grid-points*bins/s", "value": v, "unit": "grid-point*bins/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "step": r["sample"]},
+        "cpu_baseline": {"value": v, "unit": "grid-point*bins/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": v, "unit": "grid-point*bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pyipn_b200 import Context
+    from pyipn_b200._lib import OPT_LOGLIK_IMPL
+    from pyipn_b200.distributed import gather_columns, shard_bounds
+    from pyipn_b200.synth import delay_grid_workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: pyipn_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S_total = a.draws_per_gpu * world
+    w = delay_grid_workload(T=a.bins, G=a.delays, S=S_total, k=a.k)
+    lo, hi = shard_bounds(S_total, rank, world)
+    S = hi - lo
+    T, G, J = a.bins, a.delays, 2 * a.k
+    host = dict(time=w["time"], exposure=w["exposure"], counts=w["counts"], omega=w["omega"][lo:hi], a=w["a"][lo:hi],
+                b=w["b"][lo:hi], amp=w["amp"][lo:hi], bkg=w["bkg"][lo:hi], delays=w["delays"])
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}
+    ll = torch.empty((G, S), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    ctx = Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_option(OPT_LOGLIK_IMPL, a.loglik_impl)
+
+    def step_resident():
+        flush.zero_()
+        ctx.loglik_delay_grid_dev(T, d["time"].data_ptr(), d["exposure"].data_ptr(), d["counts"].data_ptr(), S, J,
+                                  d["omega"].data_ptr(), d["a"].data_ptr(), d["b"].data_ptr(), d["amp"].data_ptr(),
+                                  d["bkg"].data_ptr(), G, d["delays"].data_ptr(), ll.data_ptr())
+        if world > 1:
+            return gather_columns(ll, S_total)
+        return ll
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_resident()
+        ctx.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms, main_launches = 0.0, 0
+    ev0.record()
+    for _ in range(a.steps):
+        full = step_resident()
+        ctx.synchronize()  # also folds the per-launch event pairs of the contraction kernel into last_main_kernel
+        m, n = ctx.last_main_kernel
+        main_ms += m
+        main_launches += n
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    units_step = float(G) * float(S_total) * float(T)
+    value = units_step * a.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public host-buffer API: pinned inputs in, results out, copies inside the timed region
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in host.items()}
+    out_pinned = torch.empty((G, S), dtype=torch.float64).pin_memory()
+    pn = {k: v.numpy() for k, v in pinned.items()}
+    out_np = out_pinned.numpy()
+
+    def step_e2e():
+        ctx.loglik_delay_grid(pn["time"], pn["exposure"], pn["counts"], pn["omega"], pn["a"], pn["b"], pn["amp"], pn["bkg"],
+                              pn["delays"], out=out_np)
+        if world > 1:
+            return gather_columns(out_pinned.to(dev, non_blocking=True), S_total)
+        return out_pinned
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values()) * world
+    d2h = out_pinned.numel() * out_pinned.element_size() * world
+
+    # parity spot check of the timed result against the e2e result (same inputs, two entry points)
+    same = bool(torch.allclose(ll.cpu(), out_pinned, rtol=0, atol=1e-6))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_nominal = sms * 128 * 2 * sm_max * 1e6 / 1e12
+        fma_measured = ctx.microbench(0)
+        units_rank_step = float(G) * float(S) * float(T)
+        achieved = units_rank_step * a.steps * FLOP_PER_UNIT / (main_ms * 1e-3) / 1e12 if main_ms > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json"))).get("traffic_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": "RFF Poisson loglik grid-points*bins/s", "value": value, "unit": "grid-point*bins/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 contraction, f64 phases/reduction", "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "l2": "256 MiB memset between steps, inside the timed region",
+                       "loglik_impl": a.loglik_impl, "seed": 20261019},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": units_step * a.steps / e2e_s, "unit": "grid-point*bins/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "timer": "host perf_counter, max over ranks", "matches_resident": same},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_nominal, "unit": "TFLOP/s",
+                         "frac": (achieved / fp32_nominal) if achieved else None, "traffic": traffic,
+                         "peak_source": f"nominal FP32 FMA: {sms} SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 "
+                                        "figure); peak_fma_loop_measured is this run's FFMA loop",
+                         "peak_fma_loop_measured": fma_measured,
+                         "frac_of_measured_fma_loop": (achieved / fma_measured) if achieved else None,
+                         "algorithmic_flop_per_unit": FLOP_PER_UNIT, "kernel": "loglik contraction + fused Poisson epilogue",
+                         "kernel_launches": int(main_launches), "kernel_ms_per_launch": main_ms / max(1, main_launches),
+                         "kernel_share_of_step": main_ms / elapsed_ms if elapsed_ms else None},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            from oracle.cpu_bench import time_oracle
+
+            small = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, a.draws_per_gpu), k=a.k)
+            r = time_oracle(small)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "grid-point*bins/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

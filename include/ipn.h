@@ -57,6 +57,8 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value);
 uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx);
 /* CUDA-event time in ms spent between the first and last kernel of the most recent compute call        */
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx);
+/* summed CUDA-event time of the dominant (contraction) kernel launches of that call, and how many there were  */
+double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches);
 const char* ipn_last_error(void);
 const char* ipn_version(void);
 

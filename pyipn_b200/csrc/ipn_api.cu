@@ -49,7 +49,23 @@ static int ctx_guard(ipn_ctx* ctx) {
     return IPN_OK;
 }
 
+static cudaEvent_t next_main_event(ipn_ctx* ctx) {
+    if (ctx->main_ev_used == ctx->main_ev.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->main_ev.push_back(e);
+    }
+    return ctx->main_ev[ctx->main_ev_used++];
+}
+int main_kernel_begin(ipn_ctx* ctx) {
+    cudaEvent_t e = next_main_event(ctx);
+    if (e) IPN_CUDA_CHECK(cudaEventRecord(e, ctx->stream));
+    return IPN_OK;
+}
+int main_kernel_end(ipn_ctx* ctx) { return main_kernel_begin(ctx); }
+
 static int begin_timing(ipn_ctx* ctx) {
+    ctx->main_ev_used = 0;
     IPN_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     return IPN_OK;
 }
@@ -63,6 +79,16 @@ static int finish_timing(ipn_ctx* ctx) {
         ctx->last_kernel_ms = ms;
     else
         cudaGetLastError();
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->main_ev_used; i += 2) {
+        float m = 0.f;
+        if (cudaEventElapsedTime(&m, ctx->main_ev[i], ctx->main_ev[i + 1]) == cudaSuccess)
+            tot += m;
+        else
+            cudaGetLastError();
+    }
+    ctx->last_main_ms = tot;
+    ctx->last_main_launches = (int64_t)(ctx->main_ev_used / 2);
     return IPN_OK;
 }
 
@@ -140,6 +166,7 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->main_ev) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -184,6 +211,11 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
 
 uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches) {
+    if (!ctx) return 0.0;
+    if (launches) *launches = ctx->last_main_launches;
+    return ctx->last_main_ms;
+}
 
 // ---------------------------------------------------------------------------------------------------
 static int check_rff_args(int64_t T, const void* time, int64_t S, int64_t J, const void* omega, const void* a,

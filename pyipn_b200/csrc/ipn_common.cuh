@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/ipn.h"
 
@@ -48,6 +49,11 @@ struct ipn_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
+    // event pairs around the dominant (contraction) kernel launches of the most recent compute call
+    std::vector<cudaEvent_t> main_ev;
+    size_t main_ev_used = 0;
+    double last_main_ms = 0.0;
+    int64_t last_main_launches = 0;
     // options
     int loglik_impl = 0;
     int precise_w = 1;
@@ -80,5 +86,9 @@ int launch_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64
 int launch_sky_delays(ipn_ctx* ctx, int64_t D, const double* sc_pos, int64_t P, const double* ghat, double* delays);
 
 int run_microbench(ipn_ctx* ctx, int which, double* result);
+
+// bracket a dominant-kernel launch with events (summed by ipn_ctx_synchronize / the host entry points)
+int main_kernel_begin(ipn_ctx* ctx);
+int main_kernel_end(ipn_ctx* ctx);
 
 }  // namespace ipn

@@ -35,12 +35,39 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
+// 2^x on the FP32 pipe.  MUFU.EX2 is not usable here: measured on B200 its relative error has a MEAN of
+// -8e-9 (tools/mufu_probe.cu), and a bias b on every bin becomes b * sum_i kappa_i u_i ~ 1e-3 nats over 1e5
+// bins.  Degree-7 polynomial on [-0.5, 0.5] after magic-number rounding; coefficients are fp32 values chosen so
+// that the MEAN relative error over the interval vanishes (9e-12 in fp32 emulation; rms 2.6e-8, max 6.5e-8).
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fminf(fmaxf(x, -125.0f), 127.9f);
+    const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float xf = x - (t - 12582912.0f);
+    float p = fmaf(xf, 1.5310080925701186e-05f, 0.00015469732170458883f);
+    p = fmaf(p, xf, 0.0013333450770005584f);
+    p = fmaf(p, xf, 0.009618064388632774f);
+    p = fmaf(p, xf, 0.05550410971045494f);
+    p = fmaf(p, xf, 0.24022650718688965f);
+    p = fmaf(p, xf, 0.6931471824645996f);
+    p = fmaf(p, xf, 1.0f);
+    const int xi = __float_as_int(t) - 0x4B400000;
+    return __int_as_float(__float_as_int(p) + (xi << 23));
+}
+
+// log2(w) for w >= 1: MUFU.LG2 seed (measured mean error +4e-8 on [1,2): unusable alone, same argument as above)
+// refined by one step  y = y0 + log2e * (w 2^(-y0) - 1)  with the unbiased exp2_poly; |w 2^(-y0) - 1| < 1e-6.
+__device__ __forceinline__ float log2_refined(float w) {
+    const float y0 = lg2_approx(w);
+    const float r = fmaf(w, exp2_poly(-y0), -1.0f);
+    return fmaf(r, 1.44269504f, y0);
+}
+
 // One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u,  u = 2^x.
 __device__ __forceinline__ float poisson_term(float x, float n, float khi, float klo) {
-    const float u = ex2_approx(x);
-    // log2(1 + u): MUFU for u >= 2^-12, cubic series below (1 + u would round away most of u there)
+    const float u = exp2_poly(x);
+    // log2(1 + u): refined MUFU for u >= 2^-12, cubic series below (1 + u would round away most of u there)
     const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
-    const float lg = (u < 2.44140625e-4f) ? series : lg2_approx(1.0f + u);
+    const float lg = (u < 2.44140625e-4f) ? series : log2_refined(1.0f + u);
     const float ku = fmaf(khi, u, klo * u);
     return fmaf(n, lg, -ku);
 }

@@ -293,10 +293,12 @@ int run_loglik_grid_simt(ipn_ctx* ctx, int64_t T, const double* time, const doub
         int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
         if (grid > items) grid = items;
         if (grid > 0) {
+            main_kernel_begin(ctx);
             if (precise)
                 loglik_simt_kernel<true><<<(int)grid, NTHREADS, smem, ctx->stream>>>(p);
             else
                 loglik_simt_kernel<false><<<(int)grid, NTHREADS, smem, ctx->stream>>>(p);
+            main_kernel_end(ctx);
             ctx->launches += 1;
             IPN_CUDA_CHECK(cudaGetLastError());
         }

@@ -168,15 +168,18 @@ class Universe(object):
         tstart, tstop, dt = np.atleast_1d(tstart), np.atleast_1d(tstop), np.atleast_1d(dt)
         for n, (name, det) in enumerate(self._detectors.items()):
             lc = self._light_curves[name]
-            m = n if n < len(tstart) else 0  # universe.py:466-468 (also redirects the sc_pos row, as the reference does)
+            # universe.py:466-468 falls back to the first time selection when fewer selections than detectors are
+            # given.  (The reference reuses the loop variable for that, which also redirects its sc_pos row to 0 and
+            # leaves the other rows uninitialised; that slip is not reproduced here.)
+            m = n if n < len(tstart) else 0
             _, t, c = lc.get_binned_light_curve(tstart[m], tstop[m], dt[m])
             counts.append(c)
             times.append(np.mean([t[:-1], t[1:]], axis=0))
             exposures.append(t[1:] - t[:-1])
             n_time_bins.append(len(c))
-            sc_pos[m] = det.xyz_km
-            sc_pointing[m] = det.pointing_vec
-            effective_area[m] = det.effective_area_towards(self._grb)
+            sc_pos[n] = det.xyz_km
+            sc_pointing[n] = det.pointing_vec
+            effective_area[n] = det.effective_area_towards(self._grb)
         mx = max(n_time_bins)
         counts_stan = np.zeros((n_dets, mx), dtype=int)
         times_stan = np.zeros((n_dets, mx))

@@ -1,0 +1,138 @@
+"""CPU: host-side logic of the facade (parameter folding, binning containers, Universe data contract, generators)."""
+import numpy as np
+import pytest
+
+from oracle import ipn_oracle as orc
+
+
+def test_fold_draws_matches_oracle_fold(rff_golden):
+    from pyipn_b200 import fold_draws
+
+    g = rff_golden
+    w, a, b = fold_draws(g["B_omega1"], g["B_omega2"], g["B_beta1"], g["B_beta2"], g["B_bw"], g["B_scale"])
+    assert w.shape == (7, 100) and w.flags.c_contiguous
+    for s in range(7):
+        ow, oa, ob = orc.fold_params(g["B_omega1"][:, s], g["B_omega2"][:, s], g["B_beta1"][:, s], g["B_beta2"][:, s],
+                                     g["B_bw"][s], g["B_scale"][0, s], g["B_scale"][1, s])
+        np.testing.assert_array_equal(w[s], ow)
+        np.testing.assert_array_equal(a[s], oa)
+        np.testing.assert_array_equal(b[s], ob)
+    # single scale == both scales equal; 1-D inputs are one draw
+    w1, a1, b1 = fold_draws(g["B_omega1"][:, 0], g["B_omega2"][:, 0], g["B_beta1"][:, 0], g["B_beta2"][:, 0], 1.0, 0.3)
+    assert w1.shape == (1, 100)
+    np.testing.assert_allclose(a1[0, :50], a1[0, 50:])
+    with pytest.raises(ValueError):
+        fold_draws(np.ones((3, 2)), np.ones((3, 2)), np.ones((4, 2)), np.ones((3, 2)), 1.0, 1.0)
+
+
+def test_lightcurve_binning_matches_reference_semantics():
+    from pyipn_b200 import BinnedLightCurve, LightCurve
+
+    rng = np.random.default_rng(0)
+    src, bkg = np.sort(rng.uniform(0, 10, 500)), np.sort(rng.uniform(-5, 20, 2000))
+    lc = LightCurve(src, bkg)
+    rate, edges, counts = lc.get_binned_light_curve(-2.0, 12.0, 0.25)
+    r2, e2, c2 = orc.bin_events(np.concatenate([src, bkg]), -2.0, 12.0, 0.25)
+    np.testing.assert_array_equal(counts, c2)
+    np.testing.assert_array_equal(edges, e2)
+    blc = BinnedLightCurve.from_lightcurve(lc, -2.0, 12.0, 0.25)
+    assert blc.n_bins == len(counts) and blc.res_ms == 250.0
+    np.testing.assert_allclose(blc.exposure, 0.25)
+    assert blc.time2idx(0.0) == np.searchsorted(edges, 0.0)
+    # get_max_sn: python loop of the reference (lightcurve.py:146-173) restated literally
+    len_int = int(1000.0 // blc.res_ms)
+    cs = np.cumsum(blc.get_src_counts(500.0 * 0 + 80.0))
+    fmax, i1, i2 = 0.0, 0, cs.size
+    for i in range(cs.size - len_int):
+        dif = cs[i + len_int] - cs[i]
+        if dif > fmax:
+            fmax, i1, i2 = dif, i, i + len_int
+    assert blc.get_max_sn(1000.0, bkg_rate=80.0) == (i1, i2)
+    with pytest.raises(AssertionError):
+        BinnedLightCurve(np.zeros(3), np.zeros(3), 0, 1, 0.1)
+
+
+def test_generators_are_seeded_and_thin_correctly():
+    from pyipn_b200.possion_gen import background_poisson_generator, norris, source_poisson_generator
+
+    a = background_poisson_generator(0.0, 20.0, 0.0, 500.0, seed=5)
+    b = background_poisson_generator(0.0, 20.0, 0.0, 500.0, seed=5)
+    np.testing.assert_array_equal(a, b)
+    assert a[0] == 0.0 and np.all(np.diff(a) > 0)
+    assert abs(len(a) - 500 * 20) < 5 * np.sqrt(500 * 20)
+    # literal restatement of the reference loop (possion_gen.py:232-240) consumes the same RandomState stream
+    rs = np.random.RandomState(5)
+    t, ref = 0.0, [0.0]
+    while t < 20.0:
+        t = t - (1.0 / 500.0) * np.log(rs.rand())
+        if rs.rand() <= 1.0:
+            ref.append(t)
+    np.testing.assert_allclose(a, np.array(ref), rtol=0, atol=1e-9)
+    s = source_poisson_generator(-5.0, 30.0, 300.0, 0.0, 0.5, 4.0, seed=7)
+    assert s[0] == -5.0 and np.all(s[1:] > 0.0)  # no source photons before the pulse starts
+    x = np.linspace(-5, 30, 7001)
+    expected = np.trapezoid(norris(x, 300.0, 0.0, 0.5, 4.0), x)
+    assert abs((len(s) - 1) - expected) < 6 * np.sqrt(expected)
+    assert len(source_poisson_generator(0.0, 5.0, 300.0, 100.0, 0.5, 4.0, seed=1)) == 0  # pulse after the window
+
+
+def test_universe_from_dict_and_stan_data_contract():
+    from pyipn_b200 import Universe
+
+    d = dict(
+        seed=42,
+        grb=dict(ra=180.0, dec=30.0, distance=500.0, K=500.0, t_rise=0.5, t_decay=4.1),
+        detectors=dict(
+            det3=dict(ra=300.0, dec=-45.0, altitude=153000.0, time="2010-01-01T00:00:00", pointing=dict(ra=180.0, dec=30.0),
+                      effective_area=1.0),
+            det2=dict(ra=60.0, dec=10.0, altitude=500.0, time="2010-01-01T00:00:00", pointing=dict(ra=180.0, dec=30.0),
+                      effective_area=1.0),
+        ),
+    )
+    u = Universe.from_dict(d)
+    u.explode_grb(-10.0, 30.0)
+    assert u.T0[0] == 0.0 and 0.30 < u.T0[1] < 0.40  # notebook: 0.34328823 with astropy frames, 0.342937 plain trig
+    assert list(u.detectors.keys())[0] == "det2"  # re-ordered by arrival time
+    sd = u.to_stan_data(-5.0, 20.0, dt=0.2, k=50, n_cores=4)
+    nb = len(np.arange(-5.0, 20.0, 0.2)) - 1
+    assert sd["N_detectors"] == 2 and sd["N_time_bins"] == [nb, nb] and sd["max_N_time_bins"] == nb
+    assert sd["counts"].dtype.kind == "i" and sd["counts"].shape == (2, nb)
+    np.testing.assert_allclose(sd["exposure"], 0.2)
+    np.testing.assert_allclose(np.linalg.norm(sd["sc_pos"], axis=1), [6371.0 + 500.0, 6371.0 + 153000.0])
+    assert sd["grainsize"] == [int(np.round(nb / 4) * 0.5)] * 2 and sd["grainsize_meta"] == 1
+    # the delay the Stan model would infer from sc_pos has the same magnitude as T0 (different c constants: 1e-8 rel)
+    g = u.grb.norm_vec
+    dt = orc.time_delay(g, sd["sc_pos"][0] - sd["sc_pos"][1])
+    assert abs(abs(dt) - u.T0[1]) < 1e-6
+    # same seed -> same light curves
+    u2 = Universe.from_dict(d)
+    u2.explode_grb(-10.0, 30.0)
+    np.testing.assert_array_equal(u2.to_stan_data(-5.0, 20.0)["counts"], sd["counts"])
+
+
+def test_fit_argument_routing_without_gpu(monkeypatch):
+    """Fit.expected_rate picks dt / amplitude exactly like pyipn/fit.py:249-267 (checked by intercepting the ABI call)."""
+    import pyipn_b200.fit as fitmod
+
+    S, k = 4, 3
+    rng = np.random.default_rng(0)
+    fit = fitmod.Fit(beta1=rng.normal(size=(k, S)), beta2=rng.normal(size=(k, S)), omega=rng.normal(size=(2, k, S)),
+                     scale=np.abs(rng.normal(size=(2, S))), background=np.full((3, S), 500.0),
+                     amplitude=np.arange(2 * S, dtype=float).reshape(2, S) + 1, dt=np.arange(2 * S, dtype=float).reshape(2, S))
+    seen = {}
+
+    class Fake:
+        def rff_eval(self, time, omega, a, b, shift, amp):
+            seen.update(shift=np.array(shift), amp=np.array(amp), omega=omega)
+            return np.zeros((len(shift), len(time)))
+
+    monkeypatch.setattr(fitmod, "default_context", lambda: Fake())
+    fit.expected_rate(np.arange(5.0), 0)
+    np.testing.assert_array_equal(seen["shift"], 0.0)
+    np.testing.assert_array_equal(seen["amp"], 1.0)
+    fit.expected_rate(np.arange(5.0), 2)
+    np.testing.assert_array_equal(seen["shift"], [4.0, 5.0, 6.0, 7.0])
+    np.testing.assert_array_equal(seen["amp"], [5.0, 6.0, 7.0, 8.0])
+    assert seen["omega"].shape == (S, 2 * k)
+    with pytest.raises(AssertionError):
+        fit.expected_rate(np.arange(5.0), 3)
