@@ -162,6 +162,7 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
     ctx->draws.release();
     ctx->accum.release();
     ctx->misc.release();
+    ctx->tcdraw.release();
     for (auto& s : ctx->io) s.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

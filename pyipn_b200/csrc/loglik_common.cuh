@@ -115,4 +115,10 @@ int run_loglik_grid_simt(ipn_ctx* ctx, int64_t T, const double* time, const doub
                          int64_t S, int64_t J, const double* omega, const double* a, const double* b,
                          const DrawConst* d_dc, int64_t G, const double* delays, double* ll, bool accumulate);
 
+// tcgen05 sliced-integer implementation (loglik_tc.cu)
+bool tc_supported(int64_t J);
+int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                       int64_t S, int64_t J, const double* omega, const double* a, const double* b, const DrawConst* d_dc,
+                       int64_t G, const double* delays, double* ll, bool accumulate);
+
 }  // namespace ipn

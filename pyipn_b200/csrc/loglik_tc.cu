@@ -1,0 +1,546 @@
+// tcgen05 implementation of the delay-grid log-likelihood: exact sliced-integer contraction on the INT8 tensor
+// pipe (UTCIMMA) with int32 accumulators in TMEM, fused Poisson epilogue.
+//
+// Why tensor cores at all (north star: "only if ncu shows the contraction beats the FP32/SFU pipe"):
+// the FP32-pipe kernel (loglik_simt.cu) tops out at 200 FFMA per (grid-point x bin) -- 1.86e11 units/s at the
+// nominal FP32 peak -- and misses the 1e-3 nat tolerance at 1e5 bins because 200-400 fp32 additions leave a
+// random ~1.4e-6 error in every exponent.  Integer tensor-core accumulation is EXACT, so the contraction can
+// be done to any precision by slicing the operands into signed 8-bit digits (an Ozaki-style splitting):
+//
+//   Phi (|.| <= 1)   = (p1 2^16 + p2 2^8 + p3) 2^-22                 3 digit planes  (|error| <= 2^-23, per bin)
+//   W sigma (|.|<=1) = (w1 2^24 + w2 2^16 + w3 2^8 + w4) 2^-30        4 digit planes  (sigma = power of two)
+//   x = sum_k Phi W  = kappa [ S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5 ],  kappa = 2^-12 / sigma
+//   S2 = w1.p1   S3 = w2.p1 + w1.p2   S4 = w3.p1 + w2.p2 + w1.p3   S5 = w4.p1 + w3.p2 + w2.p3     (9 int8 GEMMs)
+//
+// (digit products of total weight < 2^-40 are dropped: < 1e-8 in x).  The additive constant log2(A/B) of the
+// draw rides along as extra K rows (Phi = 1, W = c sigma / n_rows), so x comes out of the tensor core complete.
+//
+// Mapping: MMA M = 128 trial delays (A operand = W digits, resident for a work item), MMA N = 64 time bins
+// (B operand = Phi digits + the bins' Poisson constants, streamed through a 2-stage bulk-copy ring), K = 32 per
+// UTCIMMA, 4 level accumulators x 64 columns x 2 buffers = all 512 TMEM columns.  An epilogue thread owns ONE
+// delay (TMEM lane) and walks the tile's bins (columns): the bin's counts/kappa are warp-uniform, so zero-count
+// bins skip the log without divergence, and the sum over bins is a per-thread Kahan sum -- no shuffles, no
+// per-tile atomics.  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one lane), 2..9 = epilogue.
+#include "loglik_common.cuh"
+
+namespace ipn {
+
+namespace tc {
+constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
+constexpr int TN = 64;        // bins per tile (MMA N, TMEM columns per level)
+constexpr int NLEV = 4;       // level accumulators S2..S5
+constexpr int PW = 4;         // W digit planes
+constexpr int PP = 3;         // Phi digit planes
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
+constexpr int KPAD_MAX = 224;
+constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
+constexpr int CONST_BYTES = TN * 16;  // per-bin (n, kappa_hi, kappa_lo, 0) floats appended to every Phi tile image
+constexpr uint32_t MAGIC_BITS = 0x4B400000u;  // 1.5 * 2^23
+constexpr float MAGIC = 12582912.0f;
+}  // namespace tc
+
+struct TcDraw {
+    float ks;     // kappa = 2^-12 / sigma
+    float sigma;  // power of two
+};
+
+struct TcParams {
+    const uint8_t* Wimg;  // [Sb][n_dt][a_bytes]
+    const uint8_t* Pimg;  // [Sb][n_bt][b_bytes]
+    const TcDraw* td;     // [Sb]
+    double* R;            // [Sb][Gpad]
+    int Sb, n_dt, n_bt, nchunk, tiles_per_chunk, ksteps;
+    int64_t G, Gpad;
+    uint32_t a_bytes, b_bytes, a_plane, b_plane;  // plane strides in bytes
+};
+
+// ------------------------------------------------------------------------------------------------------
+// operand images (global memory, exactly the shared-memory byte order the UMMA descriptors expect:
+// K-major, no swizzle: [plane][k/16][row][k%16], i.e. 8x16-byte core matrices contiguous (SBO = 128 B),
+// next 16-byte K chunk after all rows (LBO = rows * 16 B))
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_digits4(int q, int8_t& d1, int8_t& d2, int8_t& d3, int8_t& d4) {
+    int r = q;
+    const int e4 = ((r + 128) & 255) - 128;
+    r = (r - e4) >> 8;
+    const int e3 = ((r + 128) & 255) - 128;
+    r = (r - e3) >> 8;
+    const int e2 = ((r + 128) & 255) - 128;
+    r = (r - e2) >> 8;
+    d1 = (int8_t)r;
+    d2 = (int8_t)e2;
+    d3 = (int8_t)e3;
+    d4 = (int8_t)e4;
+}
+
+// sigma / kappa of every draw: sigma = largest power of two with sigma*max|W| <= 1 and sigma*|c| <= n_crows
+__global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const double* __restrict__ a,
+                               const double* __restrict__ b, const DrawConst* __restrict__ dc, TcDraw* __restrict__ td) {
+    const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= Sb) return;
+    const int64_t s = S0 + sl;
+    double mx = 0.0;
+    for (int j = 0; j < J; ++j) {
+        const double aj = a[s * J + j], bj = b[s * J + j];
+        mx = fmax(mx, kLog2e * sqrt(aj * aj + bj * bj));
+    }
+    const double c = fabs((double)dc[s].c_hi + (double)dc[s].c_lo);  // inf for amp == 0 (handled through the consts)
+    int e = 20;  // sigma = 2^e, start high and walk down
+    const double lim_c = (double)n_crows * (1.0 - 1e-6);
+    while (e > -6 && (ldexp(mx, e) > 1.0 || (isfinite(c) && ldexp(c, e) > lim_c))) --e;
+    TcDraw t;
+    t.sigma = (float)ldexp(1.0, e);
+    t.ks = (float)ldexp(1.0, -12 - e);
+    td[sl] = t;
+}
+
+// W digit planes of one (draw, tile of 128 delays).  One thread = one (delay row, 16-wide K chunk).
+__global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpad, const double* __restrict__ omega,
+                                                      const double* __restrict__ a, const double* __restrict__ b,
+                                                      const DrawConst* __restrict__ dc, const TcDraw* __restrict__ td,
+                                                      int64_t G, const double* __restrict__ delays, int n_dt,
+                                                      uint32_t a_bytes, uint32_t a_plane, uint8_t* __restrict__ Wimg) {
+    const int row = threadIdx.x;  // 0..127
+    const int kc = blockIdx.x;    // K chunk of 16
+    const int dt = blockIdx.y;
+    const int sl = blockIdx.z;
+    const int64_t s = S0 + sl;
+    const int64_t g = (int64_t)dt * tc::TM + row;
+    const double sigma = (double)td[sl].sigma;
+    const double cs = (double)dc[s].c_hi + (double)dc[s].c_lo;
+    const int ncrow = Kpad - 2 * J;
+    alignas(16) int8_t d[4][16];
+    const double dl = (g < G) ? delays[g] : 0.0;
+    for (int kk = 0; kk < 16; kk += 2) {
+        const int k = kc * 16 + kk;
+        int q0 = 0, q1 = 0;
+        if (g < G) {
+            if (k < 2 * J) {
+                const int j = k >> 1;
+                const double w = omega[s * J + j], aj = a[s * J + j], bj = b[s * J + j];
+                double sn, cn;
+                sincos(w * dl, &sn, &cn);
+                q0 = (int)llrint(kLog2e * (aj * cn - bj * sn) * sigma * 1073741824.0);
+                q1 = (int)llrint(kLog2e * (aj * sn + bj * cn) * sigma * 1073741824.0);
+            } else if (isfinite(cs)) {
+                // additive constant c spread exactly over the ncrow constant rows
+                const long long tot = llrint(cs * sigma * 1073741824.0);
+                const long long base = tot / ncrow, rem = tot - base * ncrow;  // |rem| < ncrow, same sign as tot
+                const int i0 = k - 2 * J, i1 = i0 + 1;
+                const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
+                q0 = (int)(base + (i0 < ar ? sg : 0));
+                q1 = (int)(base + (i1 < ar ? sg : 0));
+            }
+        }
+        split_digits4(q0, d[0][kk], d[1][kk], d[2][kk], d[3][kk]);
+        split_digits4(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[3][kk + 1]);
+    }
+    uint8_t* img = Wimg + ((int64_t)sl * n_dt + dt) * a_bytes;
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl)
+        *reinterpret_cast<int4*>(img + (size_t)pl * a_plane + ((size_t)kc * tc::TM + row) * 16) =
+            *reinterpret_cast<const int4*>(d[pl]);
+}
+
+// Phi digit planes + Poisson constants of one (draw, tile of 64 bins).  One thread = one (bin row, K chunk).
+__global__ void __launch_bounds__(64) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
+                                                     const double* __restrict__ exposure, const int64_t* __restrict__ counts,
+                                                     const double* __restrict__ omega, const DrawConst* __restrict__ dc,
+                                                     int n_bt, uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
+    const int row = threadIdx.x;  // 0..63
+    const int kc = blockIdx.x;
+    const int bt = blockIdx.y;
+    const int sl = blockIdx.z;
+    const int64_t s = S0 + sl;
+    const int64_t i = (int64_t)bt * tc::TN + row;
+    const bool valid = i < T;
+    const double t = valid ? time[i] : 0.0;
+    alignas(16) int8_t d[3][16];
+    for (int kk = 0; kk < 16; kk += 2) {
+        const int k = kc * 16 + kk;
+        int q0 = 0, q1 = 0;
+        if (valid) {
+            if (k < 2 * J) {
+                float sn, cn;
+                sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
+                q0 = __float2int_rn(cn * 4194304.0f);  // cos row
+                q1 = __float2int_rn(sn * 4194304.0f);  // sin row
+            } else {
+                q0 = q1 = 4194304;  // constant rows: Phi = 1
+            }
+        }
+        int8_t dummy;
+        split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
+        split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
+    }
+    uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+        *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
+            *reinterpret_cast<const int4*>(d[pl]);
+    if (kc == 0) {
+        const DrawConst dcs = dc[s];
+        const bool src = isfinite(dcs.c_hi);  // amp == 0: the likelihood is the constant C_s, every term is zero
+        const double kap = (valid && src) ? exposure[i] * dcs.kap : 0.0;
+        const float khi = (float)kap;
+        float4 c;
+        c.x = (valid && src) ? (float)counts[i] : 0.0f;
+        c.y = khi;
+        c.z = (float)(kap - (double)khi);
+        c.w = 0.0f;
+        *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a protocol bug must surface as a launch failure (trap), never as a hung GPU
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// 2^(xh + xl): xh exact, |xl| small; same polynomial as exp2_poly (fit interval covers |xf| <= 0.53)
+__device__ __forceinline__ float exp2_hilo(float xh, float xl) {
+    xh = fminf(fmaxf(xh, -125.0f), 127.0f);
+    const float t = xh + tc::MAGIC;
+    const float xf = (xh - (t - tc::MAGIC)) + xl;
+    float p = fmaf(xf, 1.5310080925701186e-05f, 0.00015469732170458883f);
+    p = fmaf(p, xf, 0.0013333450770005584f);
+    p = fmaf(p, xf, 0.009618064388632774f);
+    p = fmaf(p, xf, 0.05550410971045494f);
+    p = fmaf(p, xf, 0.24022650718688965f);
+    p = fmaf(p, xf, 0.6931471824645996f);
+    p = fmaf(p, xf, 1.0f);
+    const int xi = __float_as_int(t) - (int)tc::MAGIC_BITS;
+    return __int_as_float(__float_as_int(p) + (xi << 23));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB[2] = {smem + p.a_bytes, smem + p.a_bytes + p.b_bytes};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.a_bytes + 2 * (size_t)p.b_bytes);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;   // [2]
+    uint64_t* b_empty = bars + 4;  // [2]
+    uint64_t* t_full = bars + 6;   // [2]
+    uint64_t* t_empty = bars + 8;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1 + EPI_WARPS);
+            mbar_init(t_full + i, 1);
+            mbar_init(t_empty + i, EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int items_per_draw = p.nchunk * p.n_dt;
+    const int64_t n_items = (int64_t)p.Sb * items_per_draw;
+
+    if (warp == 0) {
+        // ===== producer: bulk copies global -> shared, completion on the *_full barriers =====
+        if (lane == 0) {
+            uint32_t tile_seq = 0, item_seq = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
+                const int sl = (int)(item / items_per_draw);
+                const int rem = (int)(item - (int64_t)sl * items_per_draw);
+                const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
+                mbar_wait(a_empty, (item_seq & 1) ^ 1);
+                mbar_expect_tx(a_full, p.a_bytes);
+                bulk_g2s(sA, p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes, p.a_bytes, a_full);
+                const int bt0 = chunk * p.tiles_per_chunk;
+                const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
+                for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                    const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+                    mbar_wait(b_empty + st, ph ^ 1);
+                    mbar_expect_tx(b_full + st, p.b_bytes);
+                    bulk_g2s(sB[st], p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.b_bytes, p.b_bytes, b_full + st);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one lane feeds the tensor core =====
+        if (lane == 0) {
+            // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
+            const uint32_t a_base = smem_u32(sA);
+            const uint32_t b_base[2] = {smem_u32(sB[0]), smem_u32(sB[1])};
+            uint32_t tile_seq = 0, item_seq = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
+                const int rem = (int)(item % items_per_draw);
+                const int chunk = rem / p.n_dt;
+                const int bt0 = chunk * p.tiles_per_chunk;
+                const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
+                mbar_wait(a_full, item_seq & 1);
+                for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                    const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+                    mbar_wait(b_full + st, ph);
+                    mbar_wait(t_empty + st, ph ^ 1);  // TMEM buffer index == ring stage index
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + st * (NLEV * TN);
+                    // products (W plane q, Phi plane pp) grouped by level = q + pp
+#pragma unroll
+                    for (int lev = 0; lev < NLEV; ++lev) {
+                        bool first = true;
+#pragma unroll
+                        for (int pp = 0; pp < PP; ++pp) {
+                            const int q = lev - pp;
+                            if (q < 0 || q >= PW) continue;
+                            const uint32_t a_addr = a_base + q * p.a_plane;
+                            const uint32_t b_addr = b_base[st] + pp * p.b_plane;
+                            for (int ks = 0; ks < p.ksteps; ++ks) {
+                                const uint64_t ad = make_desc(a_addr + ks * 2 * a_lbo, a_lbo, 128);
+                                const uint64_t bd = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
+                                tc_mma_i8(d0 + lev * TN, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                            }
+                            first = false;
+                        }
+                    }
+                    tc_commit(b_empty + st);  // operands of this stage consumed
+                    tc_commit(t_full + st);   // accumulators of this buffer complete
+                }
+                tc_commit(a_empty);  // every MMA that read the W tile has completed
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay Kahan sum =====
+        const int e = warp - 2;
+        const int quarter = warp & 3;          // TMEM lanes this warp may read
+        const int half = e >> 2;               // which half of the tile's bins (columns)
+        const int col0 = half * (TN / 2);
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t tile_seq = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int sl = (int)(item / items_per_draw);
+            const int rem = (int)(item - (int64_t)sl * items_per_draw);
+            const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
+            const int bt0 = chunk * p.tiles_per_chunk;
+            const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
+            const float ks = p.td[sl].ks;
+            const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
+            const float mks = -MAGIC * ks, mks8 = -MAGIC * ks8;
+            double acc = 0.0;
+            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+                mbar_wait(b_full + st, ph);  // the tile's Poisson constants are in shared memory
+                mbar_wait(t_full + st, ph);
+                tc_fence_after();
+                const float4* cst = reinterpret_cast<const float4*>(sB[st] + (size_t)PP * p.b_plane);
+                const uint32_t t0 = tmem_base + lane_addr + st * (NLEV * TN) + col0;
+                float ssum = 0.0f, scomp = 0.0f;
+#pragma unroll 1
+                for (int cc = 0; cc < TN / 2; cc += 16) {
+                    int s2[16], s3[16], s4[16], s5[16];
+                    tc_ld16(t0 + 0 * TN + cc, s2);
+                    tc_ld16(t0 + 1 * TN + cc, s3);
+                    tc_ld16(t0 + 2 * TN + cc, s4);
+                    tc_ld16(t0 + 3 * TN + cc, s5);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 c = cst[col0 + cc + j];  // warp-uniform (n, kappa_hi, kappa_lo, -)
+                        const float xh = fmaf(__int_as_float(s2[j] + (int)MAGIC_BITS), ks, mks);
+                        float xl = fmaf(__int_as_float(s3[j] + (int)MAGIC_BITS), ks8, mks8);
+                        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
+                        const float u = exp2_hilo(xh, xl);
+                        float v = -fmaf(c.y, u, c.z * u);
+                        if (c.x != 0.0f) {
+                            const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
+                            const float w = 1.0f + u;
+                            const float y0 = lg2_approx(w);
+                            const float r = fmaf(w, exp2_poly(-y0), -1.0f);
+                            const float big = fmaf(c.x, y0, fmaf(c.x * 1.44269504f, r, v));
+                            v = (u < 2.44140625e-4f) ? fmaf(c.x, series, v) : big;
+                        }
+                        // Kahan
+                        const float yk = v - scomp;
+                        const float tt = ssum + yk;
+                        scomp = (tt - ssum) - yk;
+                        ssum = tt;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(t_empty + st);
+                    mbar_arrive(b_empty + st);
+                }
+                acc += (double)ssum - (double)scomp;
+            }
+            const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
+            if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+bool tc_supported(int64_t J) { return 2 * J + tc::MIN_CROWS <= tc::KPAD_MAX; }
+
+int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                       int64_t S, int64_t J, const double* omega, const double* a, const double* b, const DrawConst* d_dc,
+                       int64_t G, const double* delays, double* ll, bool accumulate) {
+    using namespace tc;
+    if (!tc_supported(J)) {
+        set_error("tcgen05 path supports J <= %d (got %lld)", (KPAD_MAX - MIN_CROWS) / 2, (long long)J);
+        return IPN_ERR_UNSUPPORTED;
+    }
+    const int Kpad = (int)(((2 * J + MIN_CROWS + 31) / 32) * 32);
+    const int ksteps = Kpad / 32;
+    const int n_dt = (int)((G + TM - 1) / TM);
+    const int64_t Gpad = (int64_t)n_dt * TM;
+    const int n_bt = (int)((T + TN - 1) / TN);
+    const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
+    const uint32_t a_bytes = PW * a_plane, b_bytes = PP * b_plane + CONST_BYTES;
+    const size_t smem = (size_t)a_bytes + 2 * (size_t)b_bytes + 128;
+
+    // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
+    const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
+    int64_t Sbatch = ctx->draw_batch > 0 ? ctx->draw_batch : (int64_t)((6ull << 30) / (p_per_draw + w_per_draw + 1));
+    if (Sbatch < 1) Sbatch = 1;
+    if (Sbatch > S) Sbatch = S;
+    if (Sbatch > 65535) Sbatch = 65535;
+
+    int rc;
+    if ((rc = ctx->wtab.ensure((size_t)Sbatch * w_per_draw))) return rc;
+    if ((rc = ctx->misc.ensure((size_t)Sbatch * p_per_draw))) return rc;
+    if ((rc = ctx->accum.ensure((size_t)Sbatch * Gpad * sizeof(double)))) return rc;
+    if ((rc = ctx->tcdraw.ensure((size_t)Sbatch * sizeof(TcDraw)))) return rc;
+    uint8_t* d_W = ctx->wtab.as<uint8_t>();
+    uint8_t* d_P = ctx->misc.as<uint8_t>();
+    double* d_R = ctx->accum.as<double>();
+    TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
+
+    IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
+        const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
+        IPN_CUDA_CHECK(cudaMemsetAsync(d_R, 0, (size_t)Sb * Gpad * sizeof(double), ctx->stream));
+        tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_td);
+        tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
+                                                                            n_dt, a_bytes, a_plane, d_W);
+        if (n_bt > 0)
+            tc_pimg_kernel<<<dim3(Kpad / 16, n_bt, Sb), 64, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, omega,
+                                                                               d_dc, n_bt, b_bytes, b_plane, d_P);
+        ctx->launches += 3;
+        IPN_CUDA_CHECK(cudaGetLastError());
+
+        if (n_bt > 0) {
+            // split the bins of a (draw, delay tile) into chunks when there are too few items to balance the SMs
+            int nchunk = 1;
+            const int64_t base_items = (int64_t)Sb * n_dt;
+            if (base_items < 32 * (int64_t)ctx->sm_count) {
+                nchunk = (int)((32 * (int64_t)ctx->sm_count + base_items - 1) / base_items);
+                const int max_chunks = (n_bt + 7) / 8;  // keep >= 8 tiles per item
+                if (nchunk > max_chunks) nchunk = max_chunks;
+                if (nchunk < 1) nchunk = 1;
+            }
+            const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
+            nchunk = (n_bt + tiles_per_chunk - 1) / tiles_per_chunk;
+            TcParams p;
+            p.Wimg = d_W; p.Pimg = d_P; p.td = d_td; p.R = d_R;
+            p.Sb = Sb; p.n_dt = n_dt; p.n_bt = n_bt; p.nchunk = nchunk; p.tiles_per_chunk = tiles_per_chunk; p.ksteps = ksteps;
+            p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
+            const int64_t items = (int64_t)Sb * nchunk * n_dt;
+            const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+            main_kernel_begin(ctx);
+            loglik_tc_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(p);
+            main_kernel_end(ctx);
+            ctx->launches += 1;
+            IPN_CUDA_CHECK(cudaGetLastError());
+        }
+        rc = finalize_loglik(ctx, S0, Sb, S, G, Gpad, d_R, d_dc, ll, accumulate);
+        if (rc) return rc;
+    }
+    return IPN_OK;
+}
+
+}  // namespace ipn
