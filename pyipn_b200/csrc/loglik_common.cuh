@@ -37,21 +37,38 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 // 2^x on the FP32 pipe.  MUFU.EX2 is not usable here: measured on B200 its relative error has a MEAN of
 // -8e-9 (tools/mufu_probe.cu), and a bias b on every bin becomes b * sum_i kappa_i u_i ~ 1e-3 nats over 1e5
-// bins.  Degree-7 polynomial on [-0.5, 0.5] after magic-number rounding; coefficients are fp32 values chosen so
-// that the MEAN relative error over the interval vanishes (9e-12 in fp32 emulation; rms 2.6e-8, max 6.5e-8).
+// bins.  For the same reason the polynomial must not have a systematic error either: a base-2 polynomial with
+// fp32 coefficients cannot represent ln2 (2.7e-9 relative) and that alone is ~1e-4 nats.  So: z = xf ln2 with
+// ln2 as an fp32 hi/lo pair (one rounding), then e^z with EXACT leading coefficients 1, 1, 1/2 and fitted
+// c3..c7 (|z| <= 0.375; max error 5.3e-10, mean over any eighth of the interval < 2.6e-10, fp32 emulation:
+// mean -3e-11, rms 2.6e-8, max 7.2e-8).
+constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: adding it rounds to the nearest integer
+constexpr int kMagicBits = 0x4B400000;
+
+// 2^xf * 2^xi for |xf| <= 0.54; t = float whose low mantissa bits hold the integer part (xi + magic)
+__device__ __forceinline__ float exp2_core(float xf, float t) {
+    const float z = fmaf(xf, 0.693145751953125f, xf * 1.4286068203094172e-06f);
+    float p = fmaf(z, 0.00019602585234679282f, 0.0013943274971097708f);
+    p = fmaf(p, z, 0.008333928883075714f);
+    p = fmaf(p, z, 0.041666384786367416f);
+    p = fmaf(p, z, 0.166666641831398f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.0f);
+    p = fmaf(p, z, 1.0f);
+    return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - kMagicBits) << 23));
+}
+
 __device__ __forceinline__ float exp2_poly(float x) {
-    x = fminf(fmaxf(x, -125.0f), 127.9f);
-    const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-    const float xf = x - (t - 12582912.0f);
-    float p = fmaf(xf, 1.5310080925701186e-05f, 0.00015469732170458883f);
-    p = fmaf(p, xf, 0.0013333450770005584f);
-    p = fmaf(p, xf, 0.009618064388632774f);
-    p = fmaf(p, xf, 0.05550410971045494f);
-    p = fmaf(p, xf, 0.24022650718688965f);
-    p = fmaf(p, xf, 0.6931471824645996f);
-    p = fmaf(p, xf, 1.0f);
-    const int xi = __float_as_int(t) - 0x4B400000;
-    return __int_as_float(__float_as_int(p) + (xi << 23));
+    x = fminf(fmaxf(x, -125.0f), 127.0f);
+    const float t = x + kMagic;
+    return exp2_core(x - (t - kMagic), t);
+}
+
+// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04
+__device__ __forceinline__ float exp2_hilo(float xh, float xl) {
+    xh = fminf(fmaxf(xh, -125.0f), 127.0f);
+    const float t = xh + kMagic;
+    return exp2_core((xh - (t - kMagic)) + xl, t);
 }
 
 // log2(w) for w >= 1: MUFU.LG2 seed (measured mean error +4e-8 on [1,2): unusable alone, same argument as above)

@@ -31,13 +31,12 @@ constexpr int TN = 64;        // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter, each owning 16 of the tile's 64 bins
+constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
 constexpr int CONST_BYTES = TN * 16;  // per-bin (n, kappa_hi, kappa_lo, 0) floats appended to every Phi tile image
-constexpr uint32_t MAGIC_BITS = 0x4B400000u;  // 1.5 * 2^23
-constexpr float MAGIC = 12582912.0f;
 }  // namespace tc
 
 struct TcDraw {
@@ -143,43 +142,91 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
             *reinterpret_cast<const int4*>(d[pl]);
 }
 
-// Phi digit planes + Poisson constants of one (draw, tile of 64 bins).  One thread = one (bin row, K chunk).
-__global__ void __launch_bounds__(64) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
-                                                     const double* __restrict__ exposure, const int64_t* __restrict__ counts,
-                                                     const double* __restrict__ omega, const DrawConst* __restrict__ dc,
-                                                     int n_bt, uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
-    const int row = threadIdx.x;  // 0..63
-    const int kc = blockIdx.x;
-    const int bt = blockIdx.y;
-    const int sl = blockIdx.z;
-    const int64_t s = S0 + sl;
-    const int64_t i = (int64_t)bt * tc::TN + row;
-    const bool valid = i < T;
-    const double t = valid ? time[i] : 0.0;
-    alignas(16) int8_t d[3][16];
-    for (int kk = 0; kk < 16; kk += 2) {
-        const int k = kc * 16 + kk;
-        int q0 = 0, q1 = 0;
-        if (valid) {
-            if (k < 2 * J) {
-                float sn, cn;
-                sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
-                q0 = __float2int_rn(cn * 4194304.0f);  // cos row
-                q1 = __float2int_rn(sn * 4194304.0f);  // sin row
-            } else {
-                q0 = q1 = 4194304;  // constant rows: Phi = 1
-            }
-        }
-        int8_t dummy;
-        split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
-        split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
+// Bin permutation: bins with counts > 0 first, zero-count bins last (the Poisson sum does not care about the
+// order).  Tiles of the Phi image are then homogeneous, and the epilogue of an all-zero tile skips the log
+// entirely -- a per-TILE (not per-thread) decision.  Single block, deterministic (stable partition by scan).
+__global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t* __restrict__ counts, int* __restrict__ perm,
+                                                       int* __restrict__ n_nz_out) {
+    __shared__ int wsum[32];
+    __shared__ int s_total, s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt = 0;
+    for (int64_t i = tid; i < T; i += 1024) cnt += counts[i] > 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += wsum[w];
+        s_total = t;
+        s_carry = 0;
+        *n_nz_out = t;
     }
+    __syncthreads();
+    const int total = s_total;
+    for (int64_t base = 0; base < T; base += 1024) {
+        const int64_t i = base + tid;
+        const int flag = (i < T) ? (counts[i] > 0) : 0;
+        int incl = flag;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        const int nz_before = s_carry + woff + incl - flag;
+        if (i < T) perm[flag ? nz_before : (int64_t)total + (i - nz_before)] = (int)i;
+        __syncthreads();
+        if (tid == 1023) s_carry = nz_before + flag;
+        __syncthreads();
+    }
+}
+
+// Phi digit planes + Poisson constants of one (draw, tile of 64 permuted bins).
+// 256 threads: row = tid % 64, four threads per row interleave the 16-wide K chunks.
+__global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
+                                                      const double* __restrict__ exposure, const int64_t* __restrict__ counts,
+                                                      const int* __restrict__ perm, const int* __restrict__ n_nz,
+                                                      const double* __restrict__ omega, const DrawConst* __restrict__ dc,
+                                                      int n_bt, uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
+    const int row = threadIdx.x & 63;
+    const int kg = threadIdx.x >> 6;
+    const int bt = blockIdx.x;
+    const int sl = blockIdx.y;
+    const int64_t s = S0 + sl;
+    const int64_t pos = (int64_t)bt * tc::TN + row;
+    const bool valid = pos < T;
+    const int64_t i = valid ? perm[pos] : 0;
+    const double t = valid ? time[i] : 0.0;
     uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
+    for (int kc = kg; kc < Kpad / 16; kc += 4) {
+        alignas(16) int8_t d[3][16];
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl)
-        *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
-            *reinterpret_cast<const int4*>(d[pl]);
-    if (kc == 0) {
+        for (int kk = 0; kk < 16; kk += 2) {
+            const int k = kc * 16 + kk;
+            int q0 = 0, q1 = 0;
+            if (valid) {
+                if (k < 2 * J) {
+                    float sn, cn;
+                    sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
+                    q0 = __float2int_rn(cn * 4194304.0f);  // cos row
+                    q1 = __float2int_rn(sn * 4194304.0f);  // sin row
+                } else {
+                    q0 = q1 = 4194304;  // constant rows: Phi = 1
+                }
+            }
+            int8_t dummy;
+            split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
+            split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+            *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
+                *reinterpret_cast<const int4*>(d[pl]);
+    }
+    if (kg == 0) {
         const DrawConst dcs = dc[s];
         const bool src = isfinite(dcs.c_hi);  // amp == 0: the likelihood is the constant C_s, every term is zero
         const double kap = (valid && src) ? exposure[i] * dcs.kap : 0.0;
@@ -188,7 +235,7 @@ __global__ void __launch_bounds__(64) tc_pimg_kernel(int64_t S0, int J, int Kpad
         c.x = (valid && src) ? (float)counts[i] : 0.0f;
         c.y = khi;
         c.z = (float)(kap - (double)khi);
-        c.w = 0.0f;
+        c.w = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
         *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
     }
 }
@@ -262,20 +309,46 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// 2^(xh + xl): xh exact, |xl| small; same polynomial as exp2_poly (fit interval covers |xf| <= 0.53)
-__device__ __forceinline__ float exp2_hilo(float xh, float xl) {
-    xh = fminf(fmaxf(xh, -125.0f), 127.0f);
-    const float t = xh + tc::MAGIC;
-    const float xf = (xh - (t - tc::MAGIC)) + xl;
-    float p = fmaf(xf, 1.5310080925701186e-05f, 0.00015469732170458883f);
-    p = fmaf(p, xf, 0.0013333450770005584f);
-    p = fmaf(p, xf, 0.009618064388632774f);
-    p = fmaf(p, xf, 0.05550410971045494f);
-    p = fmaf(p, xf, 0.24022650718688965f);
-    p = fmaf(p, xf, 0.6931471824645996f);
-    p = fmaf(p, xf, 1.0f);
-    const int xi = __float_as_int(t) - (int)tc::MAGIC_BITS;
-    return __int_as_float(__float_as_int(p) + (xi << 23));
+// Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, Kahan sum.
+// HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
+template <bool HC>
+__device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                           const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
+                                           float mks8, float& ssum, float& scomp) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, flag)
+        // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): S2 part exact (magic-number int->float inside the FMA)
+        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
+        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
+        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
+        const float u = exp2_hilo(xh, xl);
+        const float ku = fmaf(c.y, u, c.z * u);
+        if (HC) {
+            const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
+            const float w = 1.0f + u;
+            const float y0 = lg2_approx(w);
+            const float r = fmaf(w, exp2_poly(-y0), -1.0f);
+            const float big = fmaf(c.x, y0, fmaf(c.x * 1.44269504f, r, -ku));
+            v[j] = (u < 2.44140625e-4f) ? fmaf(c.x, series, -ku) : big;
+        } else {
+            v[j] = -ku;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float yk = v[j] - scomp;
+        const float tt = ssum + yk;
+        scomp = (tt - ssum) - yk;
+        ssum = tt;
+    }
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -285,7 +358,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sB[2] = {smem + p.a_bytes, smem + p.a_bytes + p.b_bytes};
+    uint8_t* sB0 = smem + p.a_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.a_bytes + 2 * (size_t)p.b_bytes);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
@@ -338,7 +411,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
                     mbar_wait(b_empty + st, ph ^ 1);
                     mbar_expect_tx(b_full + st, p.b_bytes);
-                    bulk_g2s(sB[st], p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.b_bytes, p.b_bytes, b_full + st);
+                    bulk_g2s(sB0 + (size_t)st * p.b_bytes, p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.b_bytes, p.b_bytes, b_full + st);
                 }
             }
         }
@@ -349,7 +422,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             const uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
             const uint32_t a_base = smem_u32(sA);
-            const uint32_t b_base[2] = {smem_u32(sB[0]), smem_u32(sB[1])};
+            const uint32_t b_base0 = smem_u32(sB0);
             uint32_t tile_seq = 0, item_seq = 0;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int rem = (int)(item % items_per_draw);
@@ -372,7 +445,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                             const int q = lev - pp;
                             if (q < 0 || q >= PW) continue;
                             const uint32_t a_addr = a_base + q * p.a_plane;
-                            const uint32_t b_addr = b_base[st] + pp * p.b_plane;
+                            const uint32_t b_addr = b_base0 + st * p.b_bytes + pp * p.b_plane;
                             for (int ks = 0; ks < p.ksteps; ++ks) {
                                 const uint64_t ad = make_desc(a_addr + ks * 2 * a_lbo, a_lbo, 128);
                                 const uint64_t bd = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
@@ -389,10 +462,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         }
     } else {
         // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay Kahan sum =====
-        const int e = warp - 2;
-        const int quarter = warp & 3;          // TMEM lanes this warp may read
-        const int half = e >> 2;               // which half of the tile's bins (columns)
-        const int col0 = half * (TN / 2);
+        const int quarter = warp & 3;                // TMEM lanes this warp may read
+        const int col0 = ((warp - 2) >> 2) * EPI_COLS;  // its share of the tile's bins (columns)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -403,46 +474,29 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
             const float ks = p.td[sl].ks;
             const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
-            const float mks = -MAGIC * ks, mks8 = -MAGIC * ks8;
+            const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
             double acc = 0.0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
                 mbar_wait(b_full + st, ph);  // the tile's Poisson constants are in shared memory
                 mbar_wait(t_full + st, ph);
                 tc_fence_after();
-                const float4* cst = reinterpret_cast<const float4*>(sB[st] + (size_t)PP * p.b_plane);
+                const float4* cst = reinterpret_cast<const float4*>(sB0 + (size_t)st * p.b_bytes + (size_t)PP * p.b_plane) + col0;
+                const bool has_counts = cst[0].w != 0.0f;
                 const uint32_t t0 = tmem_base + lane_addr + st * (NLEV * TN) + col0;
                 float ssum = 0.0f, scomp = 0.0f;
 #pragma unroll 1
-                for (int cc = 0; cc < TN / 2; cc += 16) {
-                    int s2[16], s3[16], s4[16], s5[16];
-                    tc_ld16(t0 + 0 * TN + cc, s2);
-                    tc_ld16(t0 + 1 * TN + cc, s3);
-                    tc_ld16(t0 + 2 * TN + cc, s4);
-                    tc_ld16(t0 + 3 * TN + cc, s5);
+                for (int cc = 0; cc < EPI_COLS; cc += 8) {
+                    int s2[8], s3[8], s4[8], s5[8];
+                    tc_ld8(t0 + 0 * TN + cc, s2);
+                    tc_ld8(t0 + 1 * TN + cc, s3);
+                    tc_ld8(t0 + 2 * TN + cc, s4);
+                    tc_ld8(t0 + 3 * TN + cc, s5);
                     tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float4 c = cst[col0 + cc + j];  // warp-uniform (n, kappa_hi, kappa_lo, -)
-                        const float xh = fmaf(__int_as_float(s2[j] + (int)MAGIC_BITS), ks, mks);
-                        float xl = fmaf(__int_as_float(s3[j] + (int)MAGIC_BITS), ks8, mks8);
-                        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-                        const float u = exp2_hilo(xh, xl);
-                        float v = -fmaf(c.y, u, c.z * u);
-                        if (c.x != 0.0f) {
-                            const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
-                            const float w = 1.0f + u;
-                            const float y0 = lg2_approx(w);
-                            const float r = fmaf(w, exp2_poly(-y0), -1.0f);
-                            const float big = fmaf(c.x, y0, fmaf(c.x * 1.44269504f, r, v));
-                            v = (u < 2.44140625e-4f) ? fmaf(c.x, series, v) : big;
-                        }
-                        // Kahan
-                        const float yk = v - scomp;
-                        const float tt = ssum + yk;
-                        scomp = (tt - ssum) - yk;
-                        ssum = tt;
-                    }
+                    if (has_counts)
+                        epi_units8<true>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp);
+                    else
+                        epi_units8<false>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -494,6 +548,13 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     if ((rc = ctx->misc.ensure((size_t)Sbatch * p_per_draw))) return rc;
     if ((rc = ctx->accum.ensure((size_t)Sbatch * Gpad * sizeof(double)))) return rc;
     if ((rc = ctx->tcdraw.ensure((size_t)Sbatch * sizeof(TcDraw)))) return rc;
+    if ((rc = ctx->perm.ensure((size_t)(T + 1) * sizeof(int) + 16))) return rc;
+    int* d_nnz = ctx->perm.as<int>();
+    int* d_perm = d_nnz + 4;
+    if (T > 0) {
+        tc_perm_kernel<<<1, 1024, 0, ctx->stream>>>(T, counts, d_perm, d_nnz);
+        ctx->launches += 1;
+    }
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
     uint8_t* d_P = ctx->misc.as<uint8_t>();
     double* d_R = ctx->accum.as<double>();
@@ -508,8 +569,8 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
         tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
                                                                             n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
-            tc_pimg_kernel<<<dim3(Kpad / 16, n_bt, Sb), 64, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, omega,
-                                                                               d_dc, n_bt, b_bytes, b_plane, d_P);
+            tc_pimg_kernel<<<dim3(n_bt, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
+                                                                     omega, d_dc, n_bt, b_bytes, b_plane, d_P);
         ctx->launches += 3;
         IPN_CUDA_CHECK(cudaGetLastError());
 
