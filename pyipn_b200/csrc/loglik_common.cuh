@@ -71,22 +71,26 @@ __device__ __forceinline__ float exp2_hilo(float xh, float xl) {
     return exp2_core((xh - (t - kMagic)) + xl, t);
 }
 
-// log2(w) for w >= 1: MUFU.LG2 seed (measured mean error +4e-8 on [1,2): unusable alone, same argument as above)
-// refined by one step  y = y0 + log2e * (w 2^(-y0) - 1)  with the unbiased exp2_poly; |w 2^(-y0) - 1| < 1e-6.
-__device__ __forceinline__ float log2_refined(float w) {
-    const float y0 = lg2_approx(w);
-    const float r = fmaf(w, exp2_poly(-y0), -1.0f);
-    return fmaf(r, 1.44269504f, y0);
+// log2(w) for w >= 1 as an UNEVALUATED sum y0 + log2e * r:  y0 = MUFU.LG2 seed (measured mean error +4e-8 on
+// [1,2): unusable alone, same argument as above), r = w 2^(-y0) - 1 (|r| < 1e-6) from the unbiased exp2_poly.
+// The two parts must be accumulated separately: y0 + log2e r rounded back to fp32 returns y0 whenever the
+// correction is below half an ulp, i.e. it would silently drop exactly the bias it is there to remove.
+__device__ __forceinline__ void log2_parts(float w, float& y0, float& r) {
+    y0 = lg2_approx(w);
+    r = fmaf(w, exp2_poly(-y0), -1.0f);
 }
 
-// One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u,  u = 2^x.
-__device__ __forceinline__ float poisson_term(float x, float n, float khi, float klo) {
-    const float u = exp2_poly(x);
+// One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u,  u = 2^x, returned as a main part
+// (one rounding of the exact n y0 - kappa u) and a small correction that the caller sums separately.
+__device__ __forceinline__ float poisson_term(float u, float n, float khi, float klo, float& lo) {
+    const float ku = fmaf(khi, u, klo * u);
     // log2(1 + u): refined MUFU for u >= 2^-12, cubic series below (1 + u would round away most of u there)
     const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
-    const float lg = (u < 2.44140625e-4f) ? series : log2_refined(1.0f + u);
-    const float ku = fmaf(khi, u, klo * u);
-    return fmaf(n, lg, -ku);
+    float y0, r;
+    log2_parts(1.0f + u, y0, r);
+    const bool small = u < 2.44140625e-4f;
+    lo = small ? 0.0f : (n * 1.44269504f) * r;
+    return fmaf(n, small ? series : y0, -ku);
 }
 
 // sin and cos of r (|r| <= pi + eps) given as fp32 hi + lo; see rff_eval.cu for the derivation of the constants.

@@ -198,18 +198,25 @@ __global__ void __launch_bounds__(simt::NTHREADS, 3) loglik_simt_kernel(const Si
             if (kc == NCH - 1) {
                 // ---- epilogue for delay tile gt ----
                 double cs[8];
+                float lo[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) cs[q] = 0.0;
+                for (int q = 0; q < 8; ++q) {
+                    cs[q] = 0.0;
+                    lo[q] = 0.0f;
+                }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int bin = (r < 4) ? (ty * 4 + r) : (32 + ty * 4 + (r - 4));
                     const float n = s_n[bin], khi = s_khi[bin], klo = s_klo[bin];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float x = acc[r][q] + dcs.c_hi;
-                        cs[q] += (double)poisson_term(x, n, khi, klo);
+                        float l;
+                        cs[q] += (double)poisson_term(exp2_poly(acc[r][q] + dcs.c_hi), n, khi, klo, l);
+                        lo[q] += l;
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cs[q] += (double)lo[q];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 1);

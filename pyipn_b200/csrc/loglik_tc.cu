@@ -284,15 +284,37 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+template <bool ACCUM>
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACCUM)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
@@ -314,7 +336,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 template <bool HC>
 __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
                                            const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                           float mks8, float& ssum, float& scomp) {
+                                           float mks8, float& ssum, float& scomp, float& slo) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -324,16 +346,12 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
         float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
         xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
         const float u = exp2_hilo(xh, xl);
-        const float ku = fmaf(c.y, u, c.z * u);
         if (HC) {
-            const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
-            const float w = 1.0f + u;
-            const float y0 = lg2_approx(w);
-            const float r = fmaf(w, exp2_poly(-y0), -1.0f);
-            const float big = fmaf(c.x, y0, fmaf(c.x * 1.44269504f, r, -ku));
-            v[j] = (u < 2.44140625e-4f) ? fmaf(c.x, series, -ku) : big;
+            float l;
+            v[j] = poisson_term(u, c.x, c.y, c.z, l);
+            slo += l;
         } else {
-            v[j] = -ku;
+            v[j] = -fmaf(c.y, u, c.z * u);
         }
     }
 #pragma unroll
@@ -354,6 +372,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // ------------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------------
+template <int KSTEPS>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -368,7 +387,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* t_empty = bars + 8;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
+    // uniform datapath: UTCIMMA takes its descriptors from uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -416,49 +438,55 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one lane feeds the tensor core =====
-        if (lane == 0) {
-            // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 64, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
-            const uint32_t a_base = smem_u32(sA);
-            const uint32_t b_base0 = smem_u32(sB0);
-            uint32_t tile_seq = 0, item_seq = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
-                const int rem = (int)(item % items_per_draw);
-                const int chunk = rem / p.n_dt;
-                const int bt0 = chunk * p.tiles_per_chunk;
-                const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
-                mbar_wait(a_full, item_seq & 1);
-                for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                    const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
-                    mbar_wait(b_full + st, ph);
-                    mbar_wait(t_empty + st, ph ^ 1);  // TMEM buffer index == ring stage index
-                    tc_fence_after();
-                    const uint32_t d0 = tmem_base + st * (NLEV * TN);
+        // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
+        // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        constexpr uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
+        // descriptor template: LBO / SBO / version bits; the 14-bit start-address field is added per MMA
+        const uint64_t a_tmpl = make_desc(0, a_lbo, 128), b_tmpl = make_desc(0, b_lbo, 128);
+        const uint32_t a_base = smem_u32(sA) >> 4;
+        const uint32_t b_base0 = smem_u32(sB0) >> 4;
+        uint32_t tile_seq = 0, item_seq = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
+            const int rem = (int)(item % items_per_draw);
+            const int chunk = rem / p.n_dt;
+            const int bt0 = chunk * p.tiles_per_chunk;
+            const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
+            mbar_wait(a_full, item_seq & 1);
+            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+                mbar_wait(b_full + st, ph);
+                mbar_wait(t_empty + st, ph ^ 1);  // TMEM buffer index == ring stage index
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + st * (NLEV * TN);
+                const uint32_t b_base = b_base0 + st * (p.b_bytes >> 4);
+                if (elect_one()) {
                     // products (W plane q, Phi plane pp) grouped by level = q + pp
 #pragma unroll
                     for (int lev = 0; lev < NLEV; ++lev) {
-                        bool first = true;
 #pragma unroll
                         for (int pp = 0; pp < PP; ++pp) {
                             const int q = lev - pp;
                             if (q < 0 || q >= PW) continue;
-                            const uint32_t a_addr = a_base + q * p.a_plane;
-                            const uint32_t b_addr = b_base0 + st * p.b_bytes + pp * p.b_plane;
-                            for (int ks = 0; ks < p.ksteps; ++ks) {
-                                const uint64_t ad = make_desc(a_addr + ks * 2 * a_lbo, a_lbo, 128);
-                                const uint64_t bd = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
-                                tc_mma_i8(d0 + lev * TN, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                            const bool first = (pp == 0) || (lev - (pp - 1) >= PW);  // first product of this level
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks) {
+                                const uint64_t ad = a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4));
+                                const uint64_t bd = b_tmpl + (uint64_t)(b_base + pp * (p.b_plane >> 4) + ks * (2 * b_lbo >> 4));
+                                if (first && ks == 0)
+                                    tc_mma_i8<false>(d0 + lev * TN, ad, bd, idesc);
+                                else
+                                    tc_mma_i8<true>(d0 + lev * TN, ad, bd, idesc);
                             }
-                            first = false;
                         }
                     }
                     tc_commit(b_empty + st);  // operands of this stage consumed
                     tc_commit(t_full + st);   // accumulators of this buffer complete
                 }
-                tc_commit(a_empty);  // every MMA that read the W tile has completed
+                __syncwarp();
             }
+            if (elect_one()) tc_commit(a_empty);  // every MMA that read the W tile has completed
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay Kahan sum =====
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 const float4* cst = reinterpret_cast<const float4*>(sB0 + (size_t)st * p.b_bytes + (size_t)PP * p.b_plane) + col0;
                 const bool has_counts = cst[0].w != 0.0f;
                 const uint32_t t0 = tmem_base + lane_addr + st * (NLEV * TN) + col0;
-                float ssum = 0.0f, scomp = 0.0f;
+                float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
 #pragma unroll 1
                 for (int cc = 0; cc < EPI_COLS; cc += 8) {
                     int s2[8], s3[8], s4[8], s5[8];
@@ -494,9 +522,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     tc_ld8(t0 + 3 * TN + cc, s5);
                     tc_wait_ld();
                     if (has_counts)
-                        epi_units8<true>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp);
+                        epi_units8<true>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                     else
-                        epi_units8<false>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp);
+                        epi_units8<false>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -504,7 +532,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     mbar_arrive(t_empty + st);
                     mbar_arrive(b_empty + st);
                 }
-                acc += (double)ssum - (double)scomp;
+                acc += ((double)ssum - (double)scomp) + (double)slo;
             }
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
@@ -560,7 +588,17 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     double* d_R = ctx->accum.as<double>();
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
-    IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const TcParams) = nullptr;
+    switch (ksteps) {
+        case 1: kern = loglik_tc_kernel<1>; break;
+        case 2: kern = loglik_tc_kernel<2>; break;
+        case 3: kern = loglik_tc_kernel<3>; break;
+        case 4: kern = loglik_tc_kernel<4>; break;
+        case 5: kern = loglik_tc_kernel<5>; break;
+        case 6: kern = loglik_tc_kernel<6>; break;
+        default: kern = loglik_tc_kernel<7>; break;
+    }
+    IPN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
@@ -593,7 +631,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
             main_kernel_begin(ctx);
-            loglik_tc_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(p);
+            kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
             main_kernel_end(ctx);
             ctx->launches += 1;
             IPN_CUDA_CHECK(cudaGetLastError());
