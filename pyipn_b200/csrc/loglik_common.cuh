@@ -64,33 +64,34 @@ __device__ __forceinline__ float exp2_poly(float x) {
     return exp2_core(x - (t - kMagic), t);
 }
 
-// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04
+// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04.  The upper clamp
+// keeps 1 + u below 2^121 so that the log refinement below needs no clamp of its own.
 __device__ __forceinline__ float exp2_hilo(float xh, float xl) {
-    xh = fminf(fmaxf(xh, -125.0f), 127.0f);
+    xh = fminf(fmaxf(xh, -125.0f), 120.0f);
     const float t = xh + kMagic;
     return exp2_core((xh - (t - kMagic)) + xl, t);
 }
 
-// log2(w) for w >= 1 as an UNEVALUATED sum y0 + log2e * r:  y0 = MUFU.LG2 seed (measured mean error +4e-8 on
-// [1,2): unusable alone, same argument as above), r = w 2^(-y0) - 1 (|r| < 1e-6) from the unbiased exp2_poly.
-// The two parts must be accumulated separately: y0 + log2e r rounded back to fp32 returns y0 whenever the
-// correction is below half an ulp, i.e. it would silently drop exactly the bias it is there to remove.
-__device__ __forceinline__ void log2_parts(float w, float& y0, float& r) {
-    y0 = lg2_approx(w);
-    r = fmaf(w, exp2_poly(-y0), -1.0f);
-}
-
-// One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u,  u = 2^x, returned as a main part
-// (one rounding of the exact n y0 - kappa u) and a small correction that the caller sums separately.
-__device__ __forceinline__ float poisson_term(float u, float n, float khi, float klo, float& lo) {
+// One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u  as a main part (ONE rounding of the
+// exact n y0 - kappa u) plus a small correction `lo` that the caller sums separately in fp32:
+//   w = fl(1 + u),  e_w = (1 + u) - w  recovered exactly (Fast2Sum; valid for every u < 2^24),
+//   y0 = MUFU.LG2(w)  (measured mean error +4e-8 on [1,2): unusable alone, same argument as for EX2),
+//   t = 2^(-y0) from the unbiased exp2_core,  r = w t - 1  (|r| < 1e-6),
+//   log2(1 + u) = y0 + log2e (r + e_w t) + O(1e-13).
+// y0 + log2e r must NOT be rounded back into one fp32: whenever the correction is below half an ulp of y0 the
+// sum returns y0, i.e. it would silently drop exactly the bias the correction is there to remove.  The e_w term
+// also makes the tiny-u case exact (w = 1, y0 = 0, r = 0, e_w = u  ->  log2e u).
+//   nl = n log2e (precomputed per bin).
+__device__ __forceinline__ float poisson_term(float u, float n, float nl, float khi, float klo, float& lo) {
     const float ku = fmaf(khi, u, klo * u);
-    // log2(1 + u): refined MUFU for u >= 2^-12, cubic series below (1 + u would round away most of u there)
-    const float series = u * fmaf(u, fmaf(u, 0.48089835f, -0.72134752f), 1.44269504f);
-    float y0, r;
-    log2_parts(1.0f + u, y0, r);
-    const bool small = u < 2.44140625e-4f;
-    lo = small ? 0.0f : (n * 1.44269504f) * r;
-    return fmaf(n, small ? series : y0, -ku);
+    const float w = 1.0f + u;
+    const float ew = u - (w - 1.0f);
+    const float y0 = lg2_approx(w);
+    const float tm = -y0 + kMagic;
+    const float t = exp2_core(-y0 - (tm - kMagic), tm);
+    const float r = fmaf(ew, t, fmaf(w, t, -1.0f));
+    lo = nl * r;
+    return fmaf(n, y0, -ku);
 }
 
 // sin and cos of r (|r| <= pi + eps) given as fp32 hi + lo; see rff_eval.cu for the derivation of the constants.

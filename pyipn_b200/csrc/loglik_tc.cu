@@ -36,7 +36,8 @@ constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
-constexpr int CONST_BYTES = TN * 16;  // per-bin (n, kappa_hi, kappa_lo, 0) floats appended to every Phi tile image
+constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
+constexpr int NCST = 4;                    // depth of the shared-memory ring of those constant blocks
 }  // namespace tc
 
 struct TcDraw {
@@ -46,12 +47,12 @@ struct TcDraw {
 
 struct TcParams {
     const uint8_t* Wimg;  // [Sb][n_dt][a_bytes]
-    const uint8_t* Pimg;  // [Sb][n_bt][b_bytes]
+    const uint8_t* Pimg;  // [Sb][n_bt][img_bytes]: digit planes (b_dig bytes) followed by the constants block
     const TcDraw* td;     // [Sb]
     double* R;            // [Sb][Gpad]
     int Sb, n_dt, n_bt, nchunk, tiles_per_chunk, ksteps;
     int64_t G, Gpad;
-    uint32_t a_bytes, b_bytes, a_plane, b_plane;  // plane strides in bytes
+    uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -235,8 +236,14 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
         c.x = (valid && src) ? (float)counts[i] : 0.0f;
         c.y = khi;
         c.z = (float)(kap - (double)khi);
-        c.w = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
+        c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
         *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
+        if (row == 0) {
+            float4 f;
+            f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
+            f.y = f.z = f.w = 0.0f;
+            *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)tc::TN * 16) = f;
+        }
     }
 }
 
@@ -262,11 +269,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(200000u)  // suspend-time hint (ns): sleep in hardware instead of polling
             : "memory");
         if (done) return;
     }
@@ -331,7 +338,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, Kahan sum.
+// Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, compensated sum.
 // HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
 template <bool HC>
 __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
@@ -340,7 +347,7 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, flag)
+        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
         // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): S2 part exact (magic-number int->float inside the FMA)
         const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
         float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
@@ -348,19 +355,18 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
         const float u = exp2_hilo(xh, xl);
         if (HC) {
             float l;
-            v[j] = poisson_term(u, c.x, c.y, c.z, l);
+            v[j] = poisson_term(u, c.x, c.w, c.y, c.z, l);
             slo += l;
         } else {
             v[j] = -fmaf(c.y, u, c.z * u);
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float yk = v[j] - scomp;
-        const float tt = ssum + yk;
-        scomp = (tt - ssum) - yk;
-        ssum = tt;
-    }
+    // pairwise sum of the eight terms (|partial| <= 8 |v|), then ONE Kahan step into the running sum
+    const float g = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    const float yk = g - scomp;
+    const float tt = ssum + yk;
+    scomp = (tt - ssum) - yk;
+    ssum = tt;
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
@@ -377,15 +383,18 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sB0 = smem + p.a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.a_bytes + 2 * (size_t)p.b_bytes);
+    uint8_t* sB0 = smem + p.a_bytes;                                  // [2][b_dig]   Phi digit planes
+    uint8_t* sC0 = sB0 + 2 * (size_t)p.b_dig;                         // [NCST][CONST_BYTES]  Poisson constants
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC0 + NCST * CONST_BYTES);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* b_full = bars + 2;   // [2]
-    uint64_t* b_empty = bars + 4;  // [2]
-    uint64_t* t_full = bars + 6;   // [2]
-    uint64_t* t_empty = bars + 8;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* b_full = bars + 2;    // [2]
+    uint64_t* b_empty = bars + 4;   // [2]
+    uint64_t* t_full = bars + 6;    // [2]
+    uint64_t* t_empty = bars + 8;   // [2]
+    uint64_t* c_full = bars + 10;   // [NCST]
+    uint64_t* c_empty = bars + 14;  // [NCST]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
@@ -397,9 +406,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1 + EPI_WARPS);
+            mbar_init(b_empty + i, 1);
             mbar_init(t_full + i, 1);
             mbar_init(t_empty + i, EPI_WARPS);
+        }
+        for (int i = 0; i < NCST; ++i) {
+            mbar_init(c_full + i, 1);
+            mbar_init(c_empty + i, EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -430,10 +443,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 const int bt0 = chunk * p.tiles_per_chunk;
                 const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
                 for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                    const uint8_t* img = p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.img_bytes;
                     const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
-                    mbar_wait(b_empty + st, ph ^ 1);
-                    mbar_expect_tx(b_full + st, p.b_bytes);
-                    bulk_g2s(sB0 + (size_t)st * p.b_bytes, p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.b_bytes, p.b_bytes, b_full + st);
+                    mbar_wait(b_empty + st, ph ^ 1);  // released by the MMA commit alone
+                    mbar_expect_tx(b_full + st, p.b_dig);
+                    bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + st);
+                    const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
+                    mbar_wait(c_empty + cs, cph ^ 1);  // released by the epilogue warps
+                    mbar_expect_tx(c_full + cs, CONST_BYTES);
+                    bulk_g2s(sC0 + (size_t)cs * CONST_BYTES, img + p.b_dig, CONST_BYTES, c_full + cs);
                 }
             }
         }
@@ -459,7 +477,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 mbar_wait(t_empty + st, ph ^ 1);  // TMEM buffer index == ring stage index
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + st * (NLEV * TN);
-                const uint32_t b_base = b_base0 + st * (p.b_bytes >> 4);
+                const uint32_t b_base = b_base0 + st * (p.b_dig >> 4);
                 if (elect_one()) {
                     // products (W plane q, Phi plane pp) grouped by level = q + pp
 #pragma unroll
@@ -489,8 +507,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             __syncwarp();
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay Kahan sum =====
-        const int quarter = warp & 3;                // TMEM lanes this warp may read
+        // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay compensated sum =====
+        const int quarter = warp & 3;                   // TMEM lanes this warp may read
         const int col0 = ((warp - 2) >> 2) * EPI_COLS;  // its share of the tile's bins (columns)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
@@ -503,16 +521,18 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const float ks = p.td[sl].ks;
             const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
             const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
-            double acc = 0.0;
+            // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
+            float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
-                mbar_wait(b_full + st, ph);  // the tile's Poisson constants are in shared memory
+                const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
+                mbar_wait(c_full + cs, cph);  // the tile's Poisson constants are in shared memory
                 mbar_wait(t_full + st, ph);
                 tc_fence_after();
-                const float4* cst = reinterpret_cast<const float4*>(sB0 + (size_t)st * p.b_bytes + (size_t)PP * p.b_plane) + col0;
-                const bool has_counts = cst[0].w != 0.0f;
+                const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
+                const bool has_counts = cbase[TN].x != 0.0f;
+                const float4* cst = cbase + col0;
                 const uint32_t t0 = tmem_base + lane_addr + st * (NLEV * TN) + col0;
-                float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
 #pragma unroll 1
                 for (int cc = 0; cc < EPI_COLS; cc += 8) {
                     int s2[8], s3[8], s4[8], s5[8];
@@ -521,19 +541,21 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     tc_ld8(t0 + 2 * TN + cc, s4);
                     tc_ld8(t0 + 3 * TN + cc, s5);
                     tc_wait_ld();
+                    if (cc + 8 >= EPI_COLS) {
+                        // last TMEM read of this tile done: hand the accumulator buffer back before the math
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(t_empty + st);
+                    }
                     if (has_counts)
                         epi_units8<true>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                     else
                         epi_units8<false>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 }
-                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(t_empty + st);
-                    mbar_arrive(b_empty + st);
-                }
-                acc += ((double)ssum - (double)scomp) + (double)slo;
+                if (lane == 0) mbar_arrive(c_empty + cs);
             }
+            const double acc = ((double)ssum - (double)scomp) + (double)slo;
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
         }
@@ -561,8 +583,8 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const int64_t Gpad = (int64_t)n_dt * TM;
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
-    const uint32_t a_bytes = PW * a_plane, b_bytes = PP * b_plane + CONST_BYTES;
-    const size_t smem = (size_t)a_bytes + 2 * (size_t)b_bytes + 128;
+    const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
+    const size_t smem = (size_t)a_bytes + 2 * (size_t)b_dig + (size_t)NCST * CONST_BYTES + 18 * 8 + 16;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -627,7 +649,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             TcParams p;
             p.Wimg = d_W; p.Pimg = d_P; p.td = d_td; p.R = d_R;
             p.Sb = Sb; p.n_dt = n_dt; p.n_bt = n_bt; p.nchunk = nchunk; p.tiles_per_chunk = tiles_per_chunk; p.ksteps = ksteps;
-            p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
+            p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_dig = b_dig; p.img_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
             main_kernel_begin(ctx);
