@@ -163,6 +163,7 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
     ctx->accum.release();
     ctx->misc.release();
     ctx->tcdraw.release();
+    ctx->dbg.release();
     ctx->perm.release();
     for (auto& s : ctx->io) s.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

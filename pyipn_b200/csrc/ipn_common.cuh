@@ -66,6 +66,7 @@ struct ipn_ctx {
     ipn::Scratch io[12];   // staging for the host-pointer entry points
     ipn::Scratch misc;
     ipn::Scratch perm;     // bin permutation (counts > 0 first) of the tcgen05 path
+    ipn::Scratch dbg;      // pipeline wait counters (IPN_TC_DEBUG)
     ipn::Scratch tcdraw;   // per-draw scale factors of the tcgen05 path
     void* pinned = nullptr;  // pinned host bounce buffer
     size_t pinned_cap = 0;

@@ -15,29 +15,35 @@
 // (digit products of total weight < 2^-40 are dropped: < 1e-8 in x).  The additive constant log2(A/B) of the
 // draw rides along as extra K rows (Phi = 1, W = c sigma / n_rows), so x comes out of the tensor core complete.
 //
-// Mapping: MMA M = 128 trial delays (A operand = W digits, resident for a work item), MMA N = 64 time bins
-// (B operand = Phi digits + the bins' Poisson constants, streamed through a 2-stage bulk-copy ring), K = 32 per
-// UTCIMMA, 4 level accumulators x 64 columns x 2 buffers = all 512 TMEM columns.  An epilogue thread owns ONE
-// delay (TMEM lane) and walks the tile's bins (columns): the bin's counts/kappa are warp-uniform, so zero-count
-// bins skip the log without divergence, and the sum over bins is a per-thread Kahan sum -- no shuffles, no
-// per-tile atomics.  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one lane), 2..9 = epilogue.
+// Mapping: MMA M = 128 trial delays, N = 32 time bins, K = 32 per UTCIMMA.  The W digits of a work item
+// (draw, 128 delays) are staged once through shared memory into TENSOR MEMORY (tcgen05.cp, 224 columns) and
+// used as the A operand from there: with both operands in shared memory the 63 MMAs of a tile would re-read
+// the 128-row A operand every time (6 KB per 32-cycle MMA = 192 B/clk, more than shared memory delivers; measured
+// ~75 cycles per MMA).  The Phi digits (B operand, 21 KB per tile) stream through a 4-stage bulk-copy ring, the
+// tiles' Poisson constants through a separate 8-deep ring.  4 level accumulators x 32 columns x 2 buffers sit in
+// TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
+// bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
+// and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
+// Warp roles: 0 = bulk-copy producer, 1 = tcgen05.cp + MMA issuer (one elected lane), 2..17 = epilogue.
 #include "loglik_common.cuh"
 
 namespace ipn {
 
 namespace tc {
 constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
-constexpr int TN = 64;        // bins per tile (MMA N, TMEM columns per level)
+constexpr int TN = 32;        // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
-constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter, each owning 16 of the tile's 64 bins
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter, each owning 8 of the tile's 32 bins
 constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
 constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
-constexpr int NCST = 4;                    // depth of the shared-memory ring of those constant blocks
+constexpr int NCST = 8;                    // depth of the shared-memory ring of those constant blocks
+constexpr int NBST = 4;                    // depth of the Phi digit-plane ring
+constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
 }  // namespace tc
 
 struct TcDraw {
@@ -53,6 +59,7 @@ struct TcParams {
     int Sb, n_dt, n_bt, nchunk, tiles_per_chunk, ksteps;
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
+    unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -186,14 +193,14 @@ __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t*
 }
 
 // Phi digit planes + Poisson constants of one (draw, tile of 64 permuted bins).
-// 256 threads: row = tid % 64, four threads per row interleave the 16-wide K chunks.
+// 256 threads: row = tid % 32, eight threads per row interleave the 16-wide K chunks.
 __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
                                                       const double* __restrict__ exposure, const int64_t* __restrict__ counts,
                                                       const int* __restrict__ perm, const int* __restrict__ n_nz,
                                                       const double* __restrict__ omega, const DrawConst* __restrict__ dc,
                                                       int n_bt, uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
-    const int row = threadIdx.x & 63;
-    const int kg = threadIdx.x >> 6;
+    const int row = threadIdx.x & (tc::TN - 1);
+    const int kg = threadIdx.x / tc::TN;
     const int bt = blockIdx.x;
     const int sl = blockIdx.y;
     const int64_t s = S0 + sl;
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
     const int64_t i = valid ? perm[pos] : 0;
     const double t = valid ? time[i] : 0.0;
     uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
-    for (int kc = kg; kc < Kpad / 16; kc += 4) {
+    for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
         alignas(16) int8_t d[3][16];
 #pragma unroll
         for (int kk = 0; kk < 16; kk += 2) {
@@ -279,6 +286,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     __trap();
 }
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+    if (!on) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -311,6 +327,32 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
             "}" ::"r"(d_tmem),
             "l"(adesc), "l"(bdesc), "r"(idesc)
             : "memory");
+}
+// A operand from tensor memory (TS form)
+template <bool ACCUM>
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+    if (ACCUM)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
+// shared memory (matrix descriptor: 128 rows x 32 bytes, K-major core matrices) -> 128 lanes x 8 columns of TMEM
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t dst_tmem, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(dst_tmem), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -382,19 +424,19 @@ template <int KSTEPS>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;
-    uint8_t* sB0 = smem + p.a_bytes;                                  // [2][b_dig]   Phi digit planes
-    uint8_t* sC0 = sB0 + 2 * (size_t)p.b_dig;                         // [NCST][CONST_BYTES]  Poisson constants
+    uint8_t* sA = smem;                                               // staging of the W digit planes
+    uint8_t* sB0 = smem + p.a_bytes;                                  // [NBST][b_dig]  Phi digit planes
+    uint8_t* sC0 = sB0 + NBST * (size_t)p.b_dig;                      // [NCST][CONST_BYTES]  Poisson constants
     uint64_t* bars = reinterpret_cast<uint64_t*>(sC0 + NCST * CONST_BYTES);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* b_full = bars + 2;    // [2]
-    uint64_t* b_empty = bars + 4;   // [2]
-    uint64_t* t_full = bars + 6;    // [2]
-    uint64_t* t_empty = bars + 8;   // [2]
-    uint64_t* c_full = bars + 10;   // [NCST]
-    uint64_t* c_empty = bars + 14;  // [NCST]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* t_full = bars + 2;             // [2]
+    uint64_t* t_empty = bars + 4;            // [2]
+    uint64_t* b_full = bars + 6;             // [NBST]
+    uint64_t* b_empty = b_full + NBST;       // [NBST]
+    uint64_t* c_full = b_empty + NBST;       // [NCST]
+    uint64_t* c_empty = c_full + NCST;       // [NCST]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + NCST);
 
     // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
@@ -405,10 +447,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
             mbar_init(t_full + i, 1);
             mbar_init(t_empty + i, EPI_WARPS);
+        }
+        for (int i = 0; i < NBST; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
         }
         for (int i = 0; i < NCST; ++i) {
             mbar_init(c_full + i, 1);
@@ -433,50 +477,73 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         // ===== producer: bulk copies global -> shared, completion on the *_full barriers =====
         if (lane == 0) {
             uint32_t tile_seq = 0, item_seq = 0;
+            unsigned long long w_be = 0, w_ce = 0;
+            const bool dbg = p.dbg != nullptr;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int sl = (int)(item / items_per_draw);
                 const int rem = (int)(item - (int64_t)sl * items_per_draw);
                 const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
-                mbar_wait(a_empty, (item_seq & 1) ^ 1);
+                mbar_wait(a_empty, (item_seq & 1) ^ 1);  // staging buffer copied into TMEM
                 mbar_expect_tx(a_full, p.a_bytes);
                 bulk_g2s(sA, p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes, p.a_bytes, a_full);
                 const int bt0 = chunk * p.tiles_per_chunk;
                 const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
                 for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                     const uint8_t* img = p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.img_bytes;
-                    const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
-                    mbar_wait(b_empty + st, ph ^ 1);  // released by the MMA commit alone
+                    const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
+                    mbar_wait_timed(b_empty + st, ph ^ 1, w_be, dbg);  // released by the MMA commit
                     mbar_expect_tx(b_full + st, p.b_dig);
                     bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + st);
                     const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                    mbar_wait(c_empty + cs, cph ^ 1);  // released by the epilogue warps
+                    mbar_wait_timed(c_empty + cs, cph ^ 1, w_ce, dbg);  // released by the epilogue warps
                     mbar_expect_tx(c_full + cs, CONST_BYTES);
                     bulk_g2s(sC0 + (size_t)cs * CONST_BYTES, img + p.b_dig, CONST_BYTES, c_full + cs);
                 }
             }
+            if (dbg) {
+                p.dbg[blockIdx.x * 8 + 0] = w_be;
+                p.dbg[blockIdx.x * 8 + 1] = w_ce;
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
-        // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+        // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 32, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         constexpr uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
-        // descriptor template: LBO / SBO / version bits; the 14-bit start-address field is added per MMA
+        // descriptor template: LBO / SBO / version bits; the 14-bit start-address field is added per use
         const uint64_t a_tmpl = make_desc(0, a_lbo, 128), b_tmpl = make_desc(0, b_lbo, 128);
         const uint32_t a_base = smem_u32(sA) >> 4;
         const uint32_t b_base0 = smem_u32(sB0) >> 4;
         uint32_t tile_seq = 0, item_seq = 0;
+        unsigned long long w_af = 0, w_bf = 0, w_te = 0;
+        const bool dbg = p.dbg != nullptr;
+        const long long t_start = clock64();
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
             const int rem = (int)(item % items_per_draw);
             const int chunk = rem / p.n_dt;
             const int bt0 = chunk * p.tiles_per_chunk;
             const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
-            mbar_wait(a_full, item_seq & 1);
+            mbar_wait_timed(a_full, item_seq & 1, w_af, dbg);
+            tc_fence_after();
+            if (elect_one()) {
+                // W digit planes: shared -> tensor memory, 8 columns (32 K-bytes x 128 lanes) per copy.  tcgen05.cp and
+                // tcgen05.mma execute in issue order, so these land after the previous item's MMAs have read TMEM.
+#pragma unroll
+                for (int q = 0; q < PW; ++q)
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks)
+                        tc_cp_128x256b(tmem_base + (q * KSTEPS + ks) * 8,
+                                       a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4)));
+                tc_commit(a_empty);  // staging buffer free once the copies have completed
+            }
+            __syncwarp();
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
-                mbar_wait(b_full + st, ph);
-                mbar_wait(t_empty + st, ph ^ 1);  // TMEM buffer index == ring stage index
+                const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
+                const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
+                mbar_wait_timed(b_full + st, ph, w_bf, dbg);
+                mbar_wait_timed(t_empty + tb, tph ^ 1, w_te, dbg);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + st * (NLEV * TN);
+                const uint32_t d0 = tmem_base + ACC_COL0 + tb * (NLEV * TN);
                 const uint32_t b_base = b_base0 + st * (p.b_dig >> 4);
                 if (elect_one()) {
                     // products (W plane q, Phi plane pp) grouped by level = q + pp
@@ -489,22 +556,26 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                             const bool first = (pp == 0) || (lev - (pp - 1) >= PW);  // first product of this level
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
-                                const uint64_t ad = a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4));
+                                const uint32_t at = tmem_base + (q * KSTEPS + ks) * 8;
                                 const uint64_t bd = b_tmpl + (uint64_t)(b_base + pp * (p.b_plane >> 4) + ks * (2 * b_lbo >> 4));
                                 if (first && ks == 0)
-                                    tc_mma_i8<false>(d0 + lev * TN, ad, bd, idesc);
+                                    tc_mma_i8_ts<false>(d0 + lev * TN, at, bd, idesc);
                                 else
-                                    tc_mma_i8<true>(d0 + lev * TN, ad, bd, idesc);
+                                    tc_mma_i8_ts<true>(d0 + lev * TN, at, bd, idesc);
                             }
                         }
                     }
                     tc_commit(b_empty + st);  // operands of this stage consumed
-                    tc_commit(t_full + st);   // accumulators of this buffer complete
+                    tc_commit(t_full + tb);   // accumulators of this buffer complete
                 }
                 __syncwarp();
             }
-            if (elect_one()) tc_commit(a_empty);  // every MMA that read the W tile has completed
-            __syncwarp();
+        }
+        if (dbg && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 2] = w_af;
+            p.dbg[blockIdx.x * 8 + 3] = w_bf;
+            p.dbg[blockIdx.x * 8 + 4] = w_te;
+            p.dbg[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_start);
         }
     } else {
         // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay compensated sum =====
@@ -512,6 +583,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const int col0 = ((warp - 2) >> 2) * EPI_COLS;  // its share of the tile's bins (columns)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
+        unsigned long long w_cf = 0, w_tf = 0;
+        const bool dbg = p.dbg != nullptr;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int sl = (int)(item / items_per_draw);
             const int rem = (int)(item - (int64_t)sl * items_per_draw);
@@ -524,40 +597,40 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const uint32_t st = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+                const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                mbar_wait(c_full + cs, cph);  // the tile's Poisson constants are in shared memory
-                mbar_wait(t_full + st, ph);
+                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);  // the tile's Poisson constants are in shared memory
+                mbar_wait_timed(t_full + tb, tph, w_tf, dbg);
                 tc_fence_after();
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
                 const float4* cst = cbase + col0;
-                const uint32_t t0 = tmem_base + lane_addr + st * (NLEV * TN) + col0;
-#pragma unroll 1
-                for (int cc = 0; cc < EPI_COLS; cc += 8) {
-                    int s2[8], s3[8], s4[8], s5[8];
-                    tc_ld8(t0 + 0 * TN + cc, s2);
-                    tc_ld8(t0 + 1 * TN + cc, s3);
-                    tc_ld8(t0 + 2 * TN + cc, s4);
-                    tc_ld8(t0 + 3 * TN + cc, s5);
-                    tc_wait_ld();
-                    if (cc + 8 >= EPI_COLS) {
-                        // last TMEM read of this tile done: hand the accumulator buffer back before the math
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(t_empty + st);
-                    }
-                    if (has_counts)
-                        epi_units8<true>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                    else
-                        epi_units8<false>(s2, s3, s4, s5, cst + cc, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                }
+                const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + col0;
+                static_assert(EPI_COLS == 8, "one 8-column TMEM load per level per tile");
+                int s2[8], s3[8], s4[8], s5[8];
+                tc_ld8(t0 + 0 * TN, s2);
+                tc_ld8(t0 + 1 * TN, s3);
+                tc_ld8(t0 + 2 * TN, s4);
+                tc_ld8(t0 + 3 * TN, s5);
+                tc_wait_ld();
+                // the accumulator buffer is in registers now: hand it back to the MMA warp before doing the math
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + tb);
+                if (has_counts)
+                    epi_units8<true>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                else
+                    epi_units8<false>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(c_empty + cs);
             }
             const double acc = ((double)ssum - (double)scomp) + (double)slo;
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
+        }
+        if (dbg && warp == 2 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 5] = w_cf;
+            p.dbg[blockIdx.x * 8 + 6] = w_tf;
         }
     }
     tc_fence_before();
@@ -584,7 +657,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
-    const size_t smem = (size_t)a_bytes + 2 * (size_t)b_dig + (size_t)NCST * CONST_BYTES + 18 * 8 + 16;
+    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (6 + 2 * NBST + 2 * NCST) * 8 + 16;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -640,7 +713,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             const int64_t base_items = (int64_t)Sb * n_dt;
             if (base_items < 32 * (int64_t)ctx->sm_count) {
                 nchunk = (int)((32 * (int64_t)ctx->sm_count + base_items - 1) / base_items);
-                const int max_chunks = (n_bt + 7) / 8;  // keep >= 8 tiles per item
+                const int max_chunks = (n_bt + 15) / 16;  // keep >= 16 tiles per item
                 if (nchunk > max_chunks) nchunk = max_chunks;
                 if (nchunk < 1) nchunk = 1;
             }
@@ -652,11 +725,32 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_dig = b_dig; p.img_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+            p.dbg = nullptr;
+            const bool want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
+            if (want_dbg) {
+                if ((rc = ctx->dbg.ensure((size_t)grid * 8 * sizeof(unsigned long long)))) return rc;
+                IPN_CUDA_CHECK(cudaMemsetAsync(ctx->dbg.p, 0, (size_t)grid * 8 * sizeof(unsigned long long), ctx->stream));
+                p.dbg = ctx->dbg.as<unsigned long long>();
+            }
             main_kernel_begin(ctx);
             kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
             main_kernel_end(ctx);
             ctx->launches += 1;
             IPN_CUDA_CHECK(cudaGetLastError());
+            if (want_dbg) {
+                std::vector<unsigned long long> h((size_t)grid * 8);
+                IPN_CUDA_CHECK(cudaMemcpyAsync(h.data(), ctx->dbg.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int c = 0; c < grid; ++c)
+                    for (int k = 0; k < 8; ++k) m[k] += (double)h[(size_t)c * 8 + k] / grid;
+                const double tiles = (double)items * tiles_per_chunk / grid;
+                fprintf(stderr,
+                        "[ipn tc] per-CTA mean cycles: total %.3g (%.0f/tile, %.0f tiles) | producer waits b_empty %.0f c_empty %.0f | "
+                        "mma waits a_full %.0f b_full %.0f t_empty %.0f | epilogue(w2) waits c_full %.0f t_full %.0f  [per tile]\n",
+                        m[7], m[7] / tiles, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles, m[4] / tiles,
+                        m[5] / tiles, m[6] / tiles);
+            }
         }
         rc = finalize_loglik(ctx, S0, Sb, S, G, Gpad, d_R, d_dc, ll, accumulate);
         if (rc) return rc;
