@@ -24,6 +24,7 @@ IPN_ERR_UNSUPPORTED = -5
 OPT_LOGLIK_IMPL = 1
 OPT_PRECISE_W = 2
 OPT_DRAW_BATCH = 3
+OPT_HIFI = 4
 
 # every symbol include/ipn.h declares (tests/test_abi.py checks the list against the header and the .so)
 EXPORTS = (

@@ -35,7 +35,7 @@ constexpr int TN = 32;        // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
-constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter, each owning 8 of the tile's 32 bins
+constexpr int EPI_WARPS = 8;       // 2 per TMEM lane quarter, each owning 16 of the tile's 32 bins (two groups of 8)
 constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int KPAD_MAX = 224;
@@ -59,6 +59,7 @@ struct TcParams {
     int Sb, n_dt, n_bt, nchunk, tiles_per_chunk, ksteps;
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
+    const int* flags;         // [0] = #bins with counts, [1] = 1: fp64 epilogue (bright data)
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
 };
 
@@ -154,21 +155,40 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
 // order).  Tiles of the Phi image are then homogeneous, and the epilogue of an all-zero tile skips the log
 // entirely -- a per-TILE (not per-thread) decision.  Single block, deterministic (stable partition by scan).
 __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t* __restrict__ counts, int* __restrict__ perm,
-                                                       int* __restrict__ n_nz_out) {
+                                                       int* __restrict__ n_nz_out, int hifi_mode) {
     __shared__ int wsum[32];
     __shared__ int s_total, s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double wsq[32];
     int cnt = 0;
-    for (int64_t i = tid; i < T; i += 1024) cnt += counts[i] > 0;
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) wsum[warp] = cnt;
+    double sq = 0.0;
+    for (int64_t i = tid; i < T; i += 1024) {
+        const double n = (double)counts[i];
+        cnt += n > 0.0;
+        sq += n * n;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+        wsum[warp] = cnt;
+        wsq[warp] = sq;
+    }
     __syncthreads();
     if (tid == 0) {
         int t = 0;
-        for (int w = 0; w < 32; ++w) t += wsum[w];
+        double q = 0.0;
+        for (int w = 0; w < 32; ++w) {
+            t += wsum[w];
+            q += wsq[w];
+        }
         s_total = t;
         s_carry = 0;
-        *n_nz_out = t;
+        n_nz_out[0] = t;
+        // fp32 epilogue error model: rms |dll| ~ 1.5e-7 sqrt(sum n_i^2).  Above ~1.5e-4 nats predicted
+        // (bright, coarsely binned data) the kernel switches to the fp64 epilogue.  hifi_mode: 0 auto, 1 on, 2 off.
+        n_nz_out[1] = hifi_mode == 1 ? 1 : (hifi_mode == 2 ? 0 : (q > 1.0e6 ? 1 : 0));
     }
     __syncthreads();
     const int total = s_total;
@@ -411,6 +431,21 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
     ssum = tt;
 }
 
+// fp64 epilogue for bright / coarsely binned data (hundreds of counts per bin): the fp32 terms above carry
+// ~6e-8 n_i relative noise each, which exceeds 1e-3 nats once sum n_i^2 is large.  8x slower, selected per call.
+__device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8],
+                                                const int (&s5)[8], const float4* __restrict__ cst, double ksd, double& acc) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 c = cst[j];
+        const double x = ksd * ((double)s2[j] + 0.00390625 * (double)s3[j] +
+                                5.9604644775390625e-8 * ((double)s4[j] * 256.0 + (double)s5[j]));
+        const double u = exp2(x);
+        const double kap = (double)c.y + (double)c.z;
+        acc += (double)c.x * (log1p(u) * kLog2e) - kap * u;
+    }
+}
+
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -546,16 +581,17 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 const uint32_t d0 = tmem_base + ACC_COL0 + tb * (NLEV * TN);
                 const uint32_t b_base = b_base0 + st * (p.b_dig >> 4);
                 if (elect_one()) {
-                    // products (W plane q, Phi plane pp) grouped by level = q + pp
+                    // products (W plane q, Phi plane pp), level = q + pp.  K steps outermost so that consecutive MMAs
+                    // accumulate into DIFFERENT level accumulators (no back-to-back read-modify-write of one tile).
 #pragma unroll
-                    for (int lev = 0; lev < NLEV; ++lev) {
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
 #pragma unroll
                         for (int pp = 0; pp < PP; ++pp) {
-                            const int q = lev - pp;
-                            if (q < 0 || q >= PW) continue;
-                            const bool first = (pp == 0) || (lev - (pp - 1) >= PW);  // first product of this level
 #pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ++ks) {
+                            for (int lev = 0; lev < NLEV; ++lev) {
+                                const int q = lev - pp;
+                                if (q < 0 || q >= PW) continue;
+                                const bool first = (pp == 0) || (lev - (pp - 1) >= PW);  // first product of this level
                                 const uint32_t at = tmem_base + (q * KSTEPS + ks) * 8;
                                 const uint64_t bd = b_tmpl + (uint64_t)(b_base + pp * (p.b_plane >> 4) + ks * (2 * b_lbo >> 4));
                                 if (first && ks == 0)
@@ -579,8 +615,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         }
     } else {
         // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay compensated sum =====
+        // Each warp owns 16 columns of every tile as two groups of 8 with ping-pong register sets: the TMEM loads
+        // of the next group (or of the next tile's first group) are in flight while the current group's math runs.
         const int quarter = warp & 3;                   // TMEM lanes this warp may read
         const int col0 = ((warp - 2) >> 2) * EPI_COLS;  // its share of the tile's bins (columns)
+        static_assert(EPI_COLS == 16, "two groups of 8 columns per warp and tile");
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
         unsigned long long w_cf = 0, w_tf = 0;
@@ -596,35 +635,72 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
-            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+            double hacc = 0.0;
+            const bool hifi = p.flags[1] != 0;
+            const double ksd = (double)ks;
+            int a2[8], a3[8], a4[8], a5[8];  // register set A: first group of the current tile
+            int b2[8], b3[8], b4[8], b5[8];  // register set B: second group
+            if (bt0 < bt1) {
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);  // the tile's Poisson constants are in shared memory
+                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);
                 mbar_wait_timed(t_full + tb, tph, w_tf, dbg);
                 tc_fence_after();
+                const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + col0;
+                tc_ld8(t0 + 0 * TN, a2);
+                tc_ld8(t0 + 1 * TN, a3);
+                tc_ld8(t0 + 2 * TN, a4);
+                tc_ld8(t0 + 3 * TN, a5);
+                tc_wait_ld();
+            }
+            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                const uint32_t tb = tile_seq & 1;
+                const uint32_t cs = tile_seq % NCST;
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
                 const float4* cst = cbase + col0;
                 const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + col0;
-                static_assert(EPI_COLS == 8, "one 8-column TMEM load per level per tile");
-                int s2[8], s3[8], s4[8], s5[8];
-                tc_ld8(t0 + 0 * TN, s2);
-                tc_ld8(t0 + 1 * TN, s3);
-                tc_ld8(t0 + 2 * TN, s4);
-                tc_ld8(t0 + 3 * TN, s5);
+                // second group of this tile in flight while the first group's math runs
+                tc_ld8(t0 + 0 * TN + 8, b2);
+                tc_ld8(t0 + 1 * TN + 8, b3);
+                tc_ld8(t0 + 2 * TN + 8, b4);
+                tc_ld8(t0 + 3 * TN + 8, b5);
+                if (hifi)
+                    epi_units8_hifi(a2, a3, a4, a5, cst, ksd, hacc);
+                else if (has_counts)
+                    epi_units8<true>(a2, a3, a4, a5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                else
+                    epi_units8<false>(a2, a3, a4, a5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 tc_wait_ld();
-                // the accumulator buffer is in registers now: hand it back to the MMA warp before doing the math
+                // all of this warp's reads of the accumulator buffer are done: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty + tb);
-                if (has_counts)
-                    epi_units8<true>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                if (bt + 1 < bt1) {
+                    // first group of the NEXT tile in flight while this tile's second group is processed
+                    const uint32_t nseq = tile_seq + 1;
+                    const uint32_t ntb = nseq & 1, ntph = (nseq >> 1) & 1;
+                    const uint32_t ncs = nseq % NCST, ncph = (nseq / NCST) & 1;
+                    mbar_wait_timed(c_full + ncs, ncph, w_cf, dbg);
+                    mbar_wait_timed(t_full + ntb, ntph, w_tf, dbg);
+                    tc_fence_after();
+                    const uint32_t n0 = tmem_base + ACC_COL0 + lane_addr + ntb * (NLEV * TN) + col0;
+                    tc_ld8(n0 + 0 * TN, a2);
+                    tc_ld8(n0 + 1 * TN, a3);
+                    tc_ld8(n0 + 2 * TN, a4);
+                    tc_ld8(n0 + 3 * TN, a5);
+                }
+                if (hifi)
+                    epi_units8_hifi(b2, b3, b4, b5, cst + 8, ksd, hacc);
+                else if (has_counts)
+                    epi_units8<true>(b2, b3, b4, b5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 else
-                    epi_units8<false>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                    epi_units8<false>(b2, b3, b4, b5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(c_empty + cs);
+                if (bt + 1 < bt1) tc_wait_ld();
             }
-            const double acc = ((double)ssum - (double)scomp) + (double)slo;
+            const double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
         }
@@ -675,7 +751,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     int* d_nnz = ctx->perm.as<int>();
     int* d_perm = d_nnz + 4;
     if (T > 0) {
-        tc_perm_kernel<<<1, 1024, 0, ctx->stream>>>(T, counts, d_perm, d_nnz);
+        tc_perm_kernel<<<1, 1024, 0, ctx->stream>>>(T, counts, d_perm, d_nnz, ctx->hifi_mode);
         ctx->launches += 1;
     }
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
@@ -725,6 +801,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_dig = b_dig; p.img_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+            p.flags = d_nnz;
             p.dbg = nullptr;
             const bool want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
             if (want_dbg) {
