@@ -240,30 +240,49 @@ def main():
         fp32_nominal = sms * 128 * 2 * sm_max * 1e6 / 1e12
         fma_measured = ctx.microbench(0)
         units_rank_step = float(G) * float(S) * float(T)
-        achieved = units_rank_step * a.steps * FLOP_PER_UNIT / (main_ms * 1e-3) / 1e12 if main_ms > 0 else None
+        main_s = main_ms * 1e-3
+        units_timed = units_rank_step * a.steps
+        fp32_equiv = units_timed * FLOP_PER_UNIT / main_s / 1e12 if main_ms > 0 else None
+        impl = ctx.last_loglik_impl
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json"))).get("traffic_bytes_per_launch")
         except Exception:
             pass
+        common = {"kernel": "loglik contraction + fused Poisson epilogue", "kernel_launches": int(main_launches),
+                  "kernel_ms_per_launch": main_ms / max(1, main_launches),
+                  "kernel_share_of_step": main_ms / elapsed_ms if elapsed_ms else None, "traffic": traffic,
+                  "fp32_contraction_equivalent": {
+                      "note": "the north star's denominator: 400 FP32 flop per (grid-point x bin) against the FP32 FMA pipe",
+                      "achieved": fp32_equiv, "peak_nominal": fp32_nominal, "frac_of_nominal": fp32_equiv / fp32_nominal if fp32_equiv else None,
+                      "peak_fma_loop_measured": fma_measured, "frac_of_measured_fma_loop": fp32_equiv / fma_measured if fp32_equiv else None,
+                      "peak_source": f"{sms} SM x 128 lanes x 2 x {sm_max:.0f} MHz; fma loop measured in this run"}}
+        if impl == 2:
+            # tcgen05 back-end: 9 int8 digit-plane products x 224 K rows = 2016 MAC = 4032 int8 op per unit
+            ops = units_timed * 4032.0 / main_s / 1e12 if main_ms > 0 else None
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            peak = 2.0 * bf16
+            roof = {"bound": "tensor", "achieved": ops, "peak": peak, "unit": "TOP/s (int8)", "frac": ops / peak if ops else None,
+                    "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst, measured): no int8 figure is measured on this pool; "
+                                    "nominal dense int8 is 2 x bf16" if "bf16_tflops" in peaks else "2 x fallback 1590 TF/s bf16"),
+                    "algorithmic_op_per_unit": 4032.0}
+        else:
+            roof = {"bound": "fp32", "achieved": fp32_equiv, "peak": fp32_nominal, "unit": "TFLOP/s",
+                    "frac": fp32_equiv / fp32_nominal if fp32_equiv else None,
+                    "peak_source": "nominal FP32 FMA pipe (MEASURED_PEAKS.json has no FP32 figure)", "algorithmic_flop_per_unit": FLOP_PER_UNIT}
+        roof.update(common)
         line = {
             "metric": "RFF Poisson loglik grid-points*bins/s", "value": value, "unit": "grid-point*bins/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 contraction, f64 phases/reduction", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 digit planes -> int32 (exact) + f32 epilogue, f64 phases/reduction" if impl == 2 else "f32 contraction, f64 phases/reduction",
+            "data": "synthetic",
             "config": {"workload": workload_name(a, world), "l2": "256 MiB memset between steps, inside the timed region",
-                       "loglik_impl": a.loglik_impl, "seed": 20261019},
+                       "loglik_impl": {0: "auto", 1: "fp32-pipe", 2: "tcgen05"}[a.loglik_impl] + f" -> ran {impl}", "seed": 20261019},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": units_step * a.steps / e2e_s, "unit": "grid-point*bins/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "timer": "host perf_counter, max over ranks", "matches_resident": same},
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_nominal, "unit": "TFLOP/s",
-                         "frac": (achieved / fp32_nominal) if achieved else None, "traffic": traffic,
-                         "peak_source": f"nominal FP32 FMA: {sms} SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 "
-                                        "figure); peak_fma_loop_measured is this run's FFMA loop",
-                         "peak_fma_loop_measured": fma_measured,
-                         "frac_of_measured_fma_loop": (achieved / fma_measured) if achieved else None,
-                         "algorithmic_flop_per_unit": FLOP_PER_UNIT, "kernel": "loglik contraction + fused Poisson epilogue",
-                         "kernel_launches": int(main_launches), "kernel_ms_per_launch": main_ms / max(1, main_launches),
-                         "kernel_share_of_step": main_ms / elapsed_ms if elapsed_ms else None},
+            "roofline": roof,
         }
         if world == 1 and not a.no_cpu_baseline:
             from oracle.cpu_bench import time_oracle

@@ -60,6 +60,8 @@ uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx);
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx);
 /* summed CUDA-event time of the dominant (contraction) kernel launches of that call, and how many there were  */
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches);
+/* which contraction back-end the most recent log-likelihood call used: 1 = FP32 pipe, 2 = tcgen05 (0 = none yet) */
+int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx);
 const char* ipn_last_error(void);
 const char* ipn_version(void);
 

@@ -29,7 +29,7 @@ OPT_HIFI = 4
 # every symbol include/ipn.h declares (tests/test_abi.py checks the list against the header and the .so)
 EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
-    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_last_error", "ipn_version",
+    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
     "ipn_loglik_sky_grid", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
 )
@@ -73,6 +73,7 @@ def load_library():
         lib.ipn_ctx_launch_count.restype = C.c_uint64
         lib.ipn_ctx_last_kernel_ms.argtypes = [_p]
         lib.ipn_ctx_last_kernel_ms.restype = C.c_double
+        lib.ipn_ctx_last_loglik_impl.argtypes = [_p]
         lib.ipn_ctx_last_main_kernel_ms.argtypes = [_p, C.POINTER(_i64)]
         lib.ipn_ctx_last_main_kernel_ms.restype = C.c_double
         rff_args = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]
@@ -157,6 +158,10 @@ class Context:
         n = _i64(0)
         ms = float(self._lib.ipn_ctx_last_main_kernel_ms(self._h, C.byref(n)))
         return ms, int(n.value)
+
+    @property
+    def last_loglik_impl(self) -> int:
+        return int(self._lib.ipn_ctx_last_loglik_impl(self._h))
 
     def microbench(self, which: int) -> float:
         out = C.c_double(0.0)

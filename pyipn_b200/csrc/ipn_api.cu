@@ -218,6 +218,7 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
 
 uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx) { return ctx ? ctx->last_impl : 0; }
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches) {
     if (!ctx) return 0.0;
     if (launches) *launches = ctx->last_main_launches;

@@ -54,6 +54,7 @@ struct ipn_ctx {
     size_t main_ev_used = 0;
     double last_main_ms = 0.0;
     int64_t last_main_launches = 0;
+    int last_impl = 0;
     // options
     int loglik_impl = 0;
     int precise_w = 1;

@@ -144,6 +144,7 @@ int run_loglik_grid(ipn_ctx* ctx, int64_t T, const double* time, const double* e
     rc = prepare_draw_constants(ctx, S, amp, bkg, d_binc, d_dc);
     if (rc) return rc;
     const bool use_tc = ctx->loglik_impl == 2 || (ctx->loglik_impl == 0 && tc_supported(J));
+    ctx->last_impl = use_tc ? 2 : 1;
     if (use_tc) return run_loglik_grid_tc(ctx, T, time, exposure, counts, S, J, omega, a, b, d_dc, G, delays, ll, accumulate);
     return run_loglik_grid_simt(ctx, T, time, exposure, counts, S, J, omega, a, b, d_dc, G, delays, ll, accumulate);
 }
