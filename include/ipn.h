@@ -110,6 +110,16 @@ int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t 
 int ipn_poisson_counts_dev(ipn_ctx* ctx, int64_t T, const double* d_exposure, int64_t S, const double* d_rates,
                            const double* d_bkg, uint64_t seed, int64_t* d_out);
 
+/* ---- classical chi^2 cross-correlation over integer shifts (next-row N1) ---------------------------------
+ * replaces  correlate(...)  pyipn/correlation.py:247-372 (same argument meaning and order; dt_1, dt_2 in ms):
+ * light curve 1 (n1 bins: bin starts t1, background-subtracted counts c1, raw counts e1 used as variances) is
+ * shifted by i = i_beg_1 .. i_beg_1 + n_max_1 - 1 bins and re-binned onto bins i_beg_2..i_end_2 of light curve 2
+ * (n2 bins) scaled by fscale.  arr_dt, arr_chi receive n_max_1 values; the arg-min scan is left to the caller. */
+int ipn_correlate(ipn_ctx* ctx, int64_t n1, const double* t1, const double* c1, const double* e1, int64_t n2,
+                  const double* t2, const double* c2, const double* e2, int64_t i_beg_2, int64_t i_end_2,
+                  int64_t i_beg_1, int64_t n_max_1, double fscale, double dt_1, double dt_2, int64_t n_sum_2,
+                  double* arr_dt, double* arr_chi);
+
 /* ---- device micro-benchmarks used by bench.py for the roofline denominators ------------------------
  * which: 0 = FP32 FMA loop (returns TFLOP/s), 1 = MUFU.EX2 loop (returns Tops/s). */
 int ipn_microbench(ipn_ctx* ctx, int which, double* result);

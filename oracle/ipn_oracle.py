@@ -348,3 +348,88 @@ def healpix_ring_pix2vec(nside, ipix):
         st = math.sqrt(max(0.0, (1.0 - z) * (1.0 + z)))
         out[m] = (st * math.cos(phi), st * math.sin(phi), z)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# classical IPN chi^2 cross-correlation  (pyipn/correlation.py:247-372)
+# ----------------------------------------------------------------------------------------------
+def correlate(arr_t_1, arr_cnts_1, arr_cnts_err_1, arr_t_2, arr_cnts_2, arr_cnts_err_2, i_beg_2, i_end_2, i_beg_1,
+              n_max_1, fscale, dt_1, dt_2, n_sum_2=1):
+    """correlation.py:247-372, plain-Python restatement (float64, same operation order): chi^2/dof of light curve 2
+    against light curve 1 shifted by i = i_beg_1 .. i_beg_1 + n_max_1 - 1 bins with fractional re-binning.
+
+    Returns (arr_dt, arr_chi, nDOF, fRijMin, dTmin, iMin, nMin) like the reference (first minimum wins)."""
+    arr_dt = np.zeros(n_max_1)
+    arr_chi = np.zeros(n_max_1)
+    nDOF = (i_end_2 - i_beg_2) / n_sum_2
+    fRijMin, iMin, nMin, dTmin = 1e4, 0, 0, 0.0
+    n = 0
+    for i in range(i_beg_1, i_beg_1 + n_max_1):
+        fRij = 0.0
+        fT1, fT2 = float(dt_1), 0.0
+        l = i
+        fdCnt1 = fdErr1 = 0.0
+        for k in range(i_beg_2, i_end_2 + 1, n_sum_2):
+            fCnt2 = fErr2 = 0.0
+            for iSum2 in range(k, k + n_sum_2):
+                fCnt2 += arr_cnts_2[iSum2]
+                fErr2 += arr_cnts_err_2[iSum2]
+            fCnt2 *= fscale
+            fErr2 *= fscale * fscale
+            fCnt1, fErr1 = fdCnt1, fdErr1
+            while fT1 <= (fT2 + dt_2 * n_sum_2):
+                fCnt1 += arr_cnts_1[l]
+                fErr1 += arr_cnts_err_1[l]
+                fT1 += dt_1
+                l += 1
+            fdT = (fT1 - (fT2 + dt_2 * n_sum_2)) / dt_1
+            fdCnt1 = fdT * arr_cnts_1[l]
+            fCnt1 += (1.0 - fdT) * arr_cnts_1[l]
+            fdErr1 = fdT * arr_cnts_err_1[l]
+            fErr1 += (1.0 - fdT) * arr_cnts_err_1[l]
+            l += 1
+            fT1 += dt_1
+            fT2 += dt_2 * n_sum_2
+            fDif = fCnt1 - fCnt2
+            fRij += fDif * fDif / (fErr1 + fErr2)
+        fRij /= nDOF - 1
+        dT = arr_t_2[i_beg_2] - arr_t_1[i]
+        arr_dt[n], arr_chi[n] = dT, fRij
+        if fRij < fRijMin:
+            fRijMin, iMin, nMin, dTmin = fRij, i, n, dT
+        n += 1
+    return arr_dt, arr_chi, nDOF, fRijMin, dTmin, iMin, nMin
+
+
+def get_max_sn(counts, dt, dt_ms, bkg_rate=500.0):
+    """lightcurve.py:146-173: window of len_int bins with the largest background-subtracted counts (first maximum)."""
+    dt_ms_bin = dt * 1000.0
+    len_int = int(dt_ms // dt_ms_bin)
+    cs = np.cumsum(np.asarray(counts) - bkg_rate * dt)
+    fmax, i1, i2 = 0.0, 0, cs.size
+    for i in range(cs.size - len_int):
+        dif = cs[i + len_int] - cs[i]
+        if dif > fmax:
+            fmax, i1, i2 = dif, i, i + len_int
+    return i1, i2
+
+
+def dtcc_interval(arr_dt, arr_chi, nDOF, fRijMin, nMin, nSigma):
+    """correlation.py:127-171 (_get_dTcc): chi^2 confidence interval of the lag."""
+    from scipy.stats import chi2, norm
+
+    P0 = norm.cdf(nSigma) - norm.cdf(-nSigma)
+    fSigma = chi2.ppf(P0, nDOF - 1) / (nDOF - 1) - 1.0 + fRijMin
+    n = arr_chi.size
+    i = nMin
+    fRij = arr_chi[i]
+    while (i > 1) and (fRij < fSigma):
+        i -= 1
+        fRij = arr_chi[i]
+    dTupper = arr_dt[i]
+    i = nMin
+    fRij = arr_chi[i]
+    while (i < n - 1) and (fRij < fSigma):
+        i += 1
+        fRij = arr_chi[i]
+    return arr_dt[i], dTupper, fSigma

@@ -4,6 +4,7 @@ Importing the package never touches the GPU; the first compute call loads ``libi
 ``python -m pyipn_b200._build``) and creates a context on ``cuda:LOCAL_RANK``.  There is no CPU fallback.
 """
 from ._lib import Context, IpnError, default_context, load_library  # noqa: F401
+from .correlation import Correlator, correlate  # noqa: F401
 from .fit import Fit, _expeced_rate, _expeced_rate_multiscale, ppc_generator  # noqa: F401
 from .lightcurve import BinnedLightCurve, LightCurve  # noqa: F401
 from .likelihood import loglik_delay_grid, loglik_sky_grid, sky_delays, time_delay  # noqa: F401

@@ -31,7 +31,7 @@ EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
     "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
-    "ipn_loglik_sky_grid", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
+    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
 )
 
 
@@ -86,6 +86,8 @@ def load_library():
         pc_args = [_p, _i64, _p, _i64, _p, _p, C.c_uint64, _p]
         lib.ipn_poisson_counts.argtypes = pc_args
         lib.ipn_poisson_counts_dev.argtypes = pc_args
+        lib.ipn_correlate.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_double, C.c_double,
+                                      C.c_double, _i64, _p, _p]
         lib.ipn_microbench.argtypes = [_p, C.c_int, C.POINTER(C.c_double)]
         _lib = lib
         return lib
@@ -232,6 +234,19 @@ class Context:
             self._h, D, _ptr(nbins), Tmax, _ptr(time), _ptr(exposure), _ptr(counts), _ptr(sc_pos), P, _ptr(ghat), S, J,
             _ptr(omega), _ptr(a), _ptr(b), _ptr(amp), _ptr(bkg), _ptr(out)))
         return out
+
+    def correlate(self, t1, c1, e1, t2, c2, e2, i_beg_2, i_end_2, i_beg_1, n_max_1, fscale, dt_1, dt_2, n_sum_2=1):
+        t1, c1, e1 = _f64(t1).ravel(), _f64(c1).ravel(), _f64(e1).ravel()
+        t2, c2, e2 = _f64(t2).ravel(), _f64(c2).ravel(), _f64(e2).ravel()
+        n1, n2 = c1.size, c2.size
+        if e1.size != n1 or t1.size < n1 or e2.size != n2 or t2.size < n2:
+            raise ValueError("light-curve arrays have inconsistent lengths")
+        arr_dt = np.zeros(int(n_max_1))
+        arr_chi = np.zeros(int(n_max_1))
+        _check(self._lib, self._lib.ipn_correlate(self._h, n1, _ptr(t1), _ptr(c1), _ptr(e1), n2, _ptr(t2), _ptr(c2), _ptr(e2),
+                                                   int(i_beg_2), int(i_end_2), int(i_beg_1), int(n_max_1), float(fscale),
+                                                   float(dt_1), float(dt_2), int(n_sum_2), _ptr(arr_dt), _ptr(arr_chi)))
+        return arr_dt, arr_chi
 
     def poisson_counts(self, exposure, rates, bkg, seed):
         rates = np.atleast_2d(_f64(rates))

@@ -452,6 +452,41 @@ int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t 
     return IPN_OK;
 }
 
+int ipn_correlate(ipn_ctx* ctx, int64_t n1, const double* t1, const double* c1, const double* e1, int64_t n2,
+                  const double* t2, const double* c2, const double* e2, int64_t i_beg_2, int64_t i_end_2, int64_t i_beg_1,
+                  int64_t n_max_1, double fscale, double dt_1, double dt_2, int64_t n_sum_2, double* arr_dt,
+                  double* arr_chi) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(n1 > 0 && n2 > 0 && t1 && c1 && e1 && t2 && c2 && e2, "empty or NULL light curve");
+    IPN_REQUIRE(n_max_1 >= 0 && n_sum_2 >= 1, "need n_max_1 >= 0 and n_sum_2 >= 1");
+    IPN_REQUIRE(0 <= i_beg_2 && i_beg_2 <= i_end_2 && i_end_2 + n_sum_2 - 1 < n2, "light curve 2 window [%lld, %lld] outside 0..%lld",
+                (long long)i_beg_2, (long long)i_end_2, (long long)n2 - 1);
+    IPN_REQUIRE(0 <= i_beg_1 && i_beg_1 + n_max_1 <= n1, "shift range outside light curve 1");
+    IPN_REQUIRE(dt_1 > 0.0 && dt_2 > 0.0 && isfinite(fscale), "need dt_1, dt_2 > 0 and a finite scale");
+    if (n_max_1 == 0) return IPN_OK;
+    IPN_REQUIRE(arr_dt && arr_chi, "NULL output array");
+    if ((rc = h2d(ctx, ctx->io[0], t1, (size_t)n1 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[1], c1, (size_t)n1 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[2], e1, (size_t)n1 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[3], t2, (size_t)n2 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[4], c2, (size_t)n2 * 8))) return rc;
+    if ((rc = h2d(ctx, ctx->io[5], e2, (size_t)n2 * 8))) return rc;
+    if ((rc = ctx->io[6].ensure((size_t)n_max_1 * 8))) return rc;
+    if ((rc = ctx->io[7].ensure((size_t)n_max_1 * 8))) return rc;
+    begin_timing(ctx);
+    rc = launch_correlate(ctx, ctx->io[0].as<double>(), ctx->io[1].as<double>(), ctx->io[2].as<double>(), ctx->io[3].as<double>(),
+                          ctx->io[4].as<double>(), ctx->io[5].as<double>(), n1, i_beg_2, i_end_2, i_beg_1, n_max_1, fscale, dt_1,
+                          dt_2, n_sum_2, ctx->io[6].as<double>(), ctx->io[7].as<double>());
+    end_timing(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaMemcpyAsync(arr_dt, ctx->io[6].p, (size_t)n_max_1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaMemcpyAsync(arr_chi, ctx->io[7].p, (size_t)n_max_1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
 int ipn_microbench(ipn_ctx* ctx, int which, double* result) {
     int rc = ctx_guard(ctx);
     if (rc) return rc;

@@ -92,6 +92,10 @@ int launch_sky_delays(ipn_ctx* ctx, int64_t D, const double* sc_pos, int64_t P, 
 
 int run_microbench(ipn_ctx* ctx, int which, double* result);
 
+int launch_correlate(ipn_ctx* ctx, const double* t1, const double* c1, const double* e1, const double* t2, const double* c2,
+                     const double* e2, int64_t n1, int64_t i_beg_2, int64_t i_end_2, int64_t i_beg_1, int64_t n_max_1,
+                     double fscale, double dt_1, double dt_2, int64_t n_sum_2, double* arr_dt, double* arr_chi);
+
 // bracket a dominant-kernel launch with events (summed by ipn_ctx_synchronize / the host entry points)
 int main_kernel_begin(ipn_ctx* ctx);
 int main_kernel_end(ipn_ctx* ctx);
