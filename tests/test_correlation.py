@@ -90,11 +90,11 @@ def test_gpu_correlate_large_random(ctx):
     c1 = rng.poisson((prof(t1[:-1] + 3.3) + 500.0) * dt1).astype(np.float64)
     c2 = rng.poisson((prof(t2[:-1]) + 500.0) * dt2).astype(np.float64)
     s1, s2 = c1 - 500.0 * dt1, c2 - 500.0 * dt2
-    args = (t1, s1, c1, t2, s2, c2, 300, 2299, 100, 20_000, dt1 / dt2, dt1 * 1000.0, dt2 * 1000.0)
+    args = (t1, s1, c1, t2, s2, c2, 300, 2299, 100, 20_000, 1.0, dt1 * 1000.0, dt2 * 1000.0)  # re-binned lc1 ~ lc2: scale 1
     arr_dt, arr_chi = ctx.correlate(*args)
     nbest = int(np.argmin(arr_chi))
     assert abs(arr_dt[nbest] - 3.3) < 0.1
     lo = max(0, nbest - 3)
-    sub = orc.correlate(t1, s1, c1, t2, s2, c2, 300, 2299, 100 + lo, 7, dt1 / dt2, dt1 * 1000.0, dt2 * 1000.0)
+    sub = orc.correlate(t1, s1, c1, t2, s2, c2, 300, 2299, 100 + lo, 7, 1.0, dt1 * 1000.0, dt2 * 1000.0)
     np.testing.assert_allclose(arr_chi[lo:lo + 7], sub[1], rtol=1e-11)
     assert lo + sub[6] == nbest
