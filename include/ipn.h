@@ -110,6 +110,15 @@ int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t 
 int ipn_poisson_counts_dev(ipn_ctx* ctx, int64_t T, const double* d_exposure, int64_t S, const double* d_rates,
                            const double* d_bkg, uint64_t seed, int64_t* d_out);
 
+/* ---- event binning (next-row N3) ------------------------------------------------------------------------
+ * replaces  LightCurve.get_binned_light_curve  pyipn/lightcurve.py:24-47 (np.arange edges + np.histogram):
+ * the caller passes n_edges = len(np.arange(tstart, tstop, dt)) and dt = edges[1] - edges[0] (numpy fills a float arange
+ * as start + i*delta with that delta); counts receives n_edges - 1 integers, bit-identical to np.histogram. */
+int ipn_bin_events(ipn_ctx* ctx, int64_t n_events, const double* times, double tstart, double dt, int64_t n_edges,
+                   int64_t* counts);
+int ipn_bin_events_dev(ipn_ctx* ctx, int64_t n_events, const double* d_times, double tstart, double dt, int64_t n_edges,
+                       int64_t* d_counts);
+
 /* ---- classical chi^2 cross-correlation over integer shifts (next-row N1) ---------------------------------
  * replaces  correlate(...)  pyipn/correlation.py:247-372 (same argument meaning and order; dt_1, dt_2 in ms):
  * light curve 1 (n1 bins: bin starts t1, background-subtracted counts c1, raw counts e1 used as variances) is

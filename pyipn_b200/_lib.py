@@ -31,7 +31,7 @@ EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
     "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
-    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
+    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
 )
 
 
@@ -86,6 +86,8 @@ def load_library():
         pc_args = [_p, _i64, _p, _i64, _p, _p, C.c_uint64, _p]
         lib.ipn_poisson_counts.argtypes = pc_args
         lib.ipn_poisson_counts_dev.argtypes = pc_args
+        lib.ipn_bin_events.argtypes = [_p, _i64, _p, C.c_double, C.c_double, _i64, _p]
+        lib.ipn_bin_events_dev.argtypes = [_p, _i64, _p, C.c_double, C.c_double, _i64, _p]
         lib.ipn_correlate.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_double, C.c_double,
                                       C.c_double, _i64, _p, _p]
         lib.ipn_microbench.argtypes = [_p, C.c_int, C.POINTER(C.c_double)]
@@ -234,6 +236,17 @@ class Context:
             self._h, D, _ptr(nbins), Tmax, _ptr(time), _ptr(exposure), _ptr(counts), _ptr(sc_pos), P, _ptr(ghat), S, J,
             _ptr(omega), _ptr(a), _ptr(b), _ptr(amp), _ptr(bkg), _ptr(out)))
         return out
+
+    def bin_events(self, times, tstart, tstop, dt):
+        """(rate, edges, counts) with the semantics of LightCurve.get_binned_light_curve (lightcurve.py:24-47)."""
+        edges = np.arange(tstart, tstop, dt)
+        times = _f64(times).ravel()
+        counts = np.zeros(max(len(edges) - 1, 0), dtype=np.int64)
+        if len(edges) >= 2:
+            # numpy fills a float arange as start + i*delta with delta = edges[1] - edges[0] (not dt itself)
+            _check(self._lib, self._lib.ipn_bin_events(self._h, times.size, _ptr(times), float(edges[0]),
+                                                        float(edges[1] - edges[0]), len(edges), _ptr(counts)))
+        return counts / float(dt), edges, counts
 
     def correlate(self, t1, c1, e1, t2, c2, e2, i_beg_2, i_end_2, i_beg_1, n_max_1, fscale, dt_1, dt_2, n_sum_2=1):
         t1, c1, e1 = _f64(t1).ravel(), _f64(c1).ravel(), _f64(e1).ravel()

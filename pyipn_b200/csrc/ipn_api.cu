@@ -452,6 +452,33 @@ int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t 
     return IPN_OK;
 }
 
+int ipn_bin_events_dev(ipn_ctx* ctx, int64_t n_events, const double* times, double tstart, double dt, int64_t n_edges,
+                       int64_t* counts) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(n_events >= 0 && n_edges >= 2 && dt > 0.0 && isfinite(tstart), "need n_events >= 0, n_edges >= 2, dt > 0");
+    IPN_REQUIRE(counts && (n_events == 0 || times), "NULL array argument");
+    return launch_bin_events(ctx, n_events, times, tstart, dt, n_edges, counts);
+}
+
+int ipn_bin_events(ipn_ctx* ctx, int64_t n_events, const double* times, double tstart, double dt, int64_t n_edges,
+                   int64_t* counts) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(n_events >= 0 && n_edges >= 2 && dt > 0.0 && isfinite(tstart), "need n_events >= 0, n_edges >= 2, dt > 0");
+    IPN_REQUIRE(counts && (n_events == 0 || times), "NULL array argument");
+    if ((rc = h2d(ctx, ctx->io[0], times, (size_t)n_events * 8))) return rc;
+    if ((rc = ctx->io[1].ensure((size_t)(n_edges - 1) * 8))) return rc;
+    begin_timing(ctx);
+    rc = launch_bin_events(ctx, n_events, ctx->io[0].as<double>(), tstart, dt, n_edges, ctx->io[1].as<int64_t>());
+    end_timing(ctx);
+    if (rc) return rc;
+    IPN_CUDA_CHECK(cudaMemcpyAsync(counts, ctx->io[1].p, (size_t)(n_edges - 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx);
+    return IPN_OK;
+}
+
 int ipn_correlate(ipn_ctx* ctx, int64_t n1, const double* t1, const double* c1, const double* e1, int64_t n2,
                   const double* t2, const double* c2, const double* e2, int64_t i_beg_2, int64_t i_end_2, int64_t i_beg_1,
                   int64_t n_max_1, double fscale, double dt_1, double dt_2, int64_t n_sum_2, double* arr_dt,

@@ -14,7 +14,12 @@ class LightCurve(object):
         self._source_arrival_time = source_arrival_times
         self._bkg_arrival_times = bkg_arrival_times
 
-    def get_binned_light_curve(self, tstart, tstop, dt):
+    def get_binned_light_curve(self, tstart, tstop, dt, device=False):
+        """lightcurve.py:24-47.  ``device=True`` bins on the GPU (``ipn_bin_events``, bit-identical counts)."""
+        if device:
+            from ._lib import default_context
+
+            return default_context().bin_events(self._arrival_times, tstart, tstop, dt)
         bins = np.arange(tstart, tstop, dt)
         counts, edges = np.histogram(self._arrival_times, bins=bins)
         rate = counts / float(dt)

@@ -121,3 +121,21 @@ def test_config5_population_reduced(ctx):
             exp = orc.loglik_delay_grid(counts[d], mid, expo, w, a, b, amp[d:d + 1], [500.0], delays[sub])
             assert np.abs(ll[sub] - exp).max() < ATOL
             assert abs(delays[best] - true[d]) < 0.02  # a bright burst localises the delay to a few grid steps
+
+
+def test_device_binning_is_bit_identical_to_numpy_histogram(ctx):
+    """Next-row N3: ipn_bin_events == np.histogram(times, np.arange(tstart, tstop, dt)) incl. edge conventions."""
+    from pyipn_b200 import LightCurve
+
+    rng = np.random.default_rng(8)
+    for tstart, tstop, dt in ((-10.0, 40.0, 0.2), (0.0, 100.0, 1e-3), (-3.3, 7.7, 0.037)):
+        edges = np.arange(tstart, tstop, dt)
+        times = np.concatenate([rng.uniform(tstart - 1.0, tstop + 1.0, 200_000), edges, edges[1:] - 1e-12, edges[:-1] + 1e-12,
+                                [edges[-1], np.nextafter(edges[-1], np.inf), np.nan]])
+        lc = LightCurve(times[:1000], times[1000:])
+        rate, e, counts = lc.get_binned_light_curve(tstart, tstop, dt, device=True)
+        ref_rate, ref_e, ref_counts = lc.get_binned_light_curve(tstart, tstop, dt)
+        np.testing.assert_array_equal(counts, ref_counts)
+        np.testing.assert_array_equal(e, ref_e)
+        np.testing.assert_array_equal(rate, ref_rate)
+    assert ctx.bin_events(np.zeros(0), 0.0, 1.0, 0.1)[2].sum() == 0
