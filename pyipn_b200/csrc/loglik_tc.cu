@@ -24,7 +24,7 @@
 // TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
-// Warp roles: 0 = bulk-copy producer, 1 = tcgen05.cp + MMA issuer (one elected lane), 2..17 = epilogue.
+// Warp roles: 0 = bulk-copy producer, 1 = tcgen05.cp + MMA issuer (one elected lane), 2..13 = epilogue.
 #include "loglik_common.cuh"
 
 namespace ipn {
@@ -35,8 +35,10 @@ constexpr int TN = 32;        // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
-constexpr int EPI_WARPS = 8;       // 2 per TMEM lane quarter, each owning 16 of the tile's 32 bins (two groups of 8)
-constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
+constexpr int EPI_WARPS = 12;      // 3 per TMEM lane quarter (and per SM sub-partition) rotating over 8-column groups
+constexpr int EPI_SLOTS = EPI_WARPS / 4;
+constexpr int GROUPS = TN / 8;     // 8-column groups per tile
+constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, group) and tile
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
@@ -296,11 +298,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(200000u)  // suspend-time hint (ns): sleep in hardware instead of polling
+            : "r"(addr), "r"(parity)  // no suspend-time hint: with one ptxas emits NANOSLEEP back-off, whose wake-up
+                                       // is not tied to the barrier and adds hundreds of cycles to every hand-over
             : "memory");
         if (done) return;
     }
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, EPI_WARPS);
+            mbar_init(t_empty + i, EPI_ARRIVALS);
         }
         for (int i = 0; i < NBST; ++i) {
             mbar_init(b_full + i, 1);
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         }
         for (int i = 0; i < NCST; ++i) {
             mbar_init(c_full + i, 1);
-            mbar_init(c_empty + i, EPI_WARPS);
+            mbar_init(c_empty + i, EPI_ARRIVALS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -615,11 +618,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         }
     } else {
         // ===== epilogue: TMEM -> registers -> Poisson terms -> per-delay compensated sum =====
-        // Each warp owns 16 columns of every tile as two groups of 8 with ping-pong register sets: the TMEM loads
-        // of the next group (or of the next tile's first group) are in flight while the current group's math runs.
-        const int quarter = warp & 3;                   // TMEM lanes this warp may read
-        const int col0 = ((warp - 2) >> 2) * EPI_COLS;  // its share of the tile's bins (columns)
-        static_assert(EPI_COLS == 16, "two groups of 8 columns per warp and tile");
+        // Work unit = (tile, group of 8 columns).  The three warps of a lane quarter take the groups round-robin
+        // (global group index mod 3), so at any time they sit in different phases (barrier wait / TMEM load / math)
+        // and cover one another's latencies; every (quarter, group) arrives once per tile on t_empty / c_empty.
+        const int quarter = warp & 3;        // TMEM lanes this warp may read
+        const int slot = (warp - 2) >> 2;    // 0..2
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
         unsigned long long w_cf = 0, w_tf = 0;
@@ -638,67 +641,39 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             double hacc = 0.0;
             const bool hifi = p.flags[1] != 0;
             const double ksd = (double)ks;
-            int a2[8], a3[8], a4[8], a5[8];  // register set A: first group of the current tile
-            int b2[8], b3[8], b4[8], b5[8];  // register set B: second group
-            if (bt0 < bt1) {
+            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);
+                // groups of this tile that belong to this warp: (tile_seq * GROUPS + cg) % EPI_SLOTS == slot
+                int cg = (int)((slot + EPI_SLOTS - (tile_seq * GROUPS) % EPI_SLOTS) % EPI_SLOTS);
+                if (cg >= GROUPS) continue;
+                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);  // the tile's Poisson constants are in shared memory
                 mbar_wait_timed(t_full + tb, tph, w_tf, dbg);
                 tc_fence_after();
-                const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + col0;
-                tc_ld8(t0 + 0 * TN, a2);
-                tc_ld8(t0 + 1 * TN, a3);
-                tc_ld8(t0 + 2 * TN, a4);
-                tc_ld8(t0 + 3 * TN, a5);
-                tc_wait_ld();
-            }
-            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const uint32_t tb = tile_seq & 1;
-                const uint32_t cs = tile_seq % NCST;
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
-                const float4* cst = cbase + col0;
-                const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + col0;
-                // second group of this tile in flight while the first group's math runs
-                tc_ld8(t0 + 0 * TN + 8, b2);
-                tc_ld8(t0 + 1 * TN + 8, b3);
-                tc_ld8(t0 + 2 * TN + 8, b4);
-                tc_ld8(t0 + 3 * TN + 8, b5);
-                if (hifi)
-                    epi_units8_hifi(a2, a3, a4, a5, cst, ksd, hacc);
-                else if (has_counts)
-                    epi_units8<true>(a2, a3, a4, a5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                else
-                    epi_units8<false>(a2, a3, a4, a5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                tc_wait_ld();
-                // all of this warp's reads of the accumulator buffer are done: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + tb);
-                if (bt + 1 < bt1) {
-                    // first group of the NEXT tile in flight while this tile's second group is processed
-                    const uint32_t nseq = tile_seq + 1;
-                    const uint32_t ntb = nseq & 1, ntph = (nseq >> 1) & 1;
-                    const uint32_t ncs = nseq % NCST, ncph = (nseq / NCST) & 1;
-                    mbar_wait_timed(c_full + ncs, ncph, w_cf, dbg);
-                    mbar_wait_timed(t_full + ntb, ntph, w_tf, dbg);
-                    tc_fence_after();
-                    const uint32_t n0 = tmem_base + ACC_COL0 + lane_addr + ntb * (NLEV * TN) + col0;
-                    tc_ld8(n0 + 0 * TN, a2);
-                    tc_ld8(n0 + 1 * TN, a3);
-                    tc_ld8(n0 + 2 * TN, a4);
-                    tc_ld8(n0 + 3 * TN, a5);
+                for (; cg < GROUPS; cg += EPI_SLOTS) {
+                    const float4* cst = cbase + cg * 8;
+                    const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * 8;
+                    int s2[8], s3[8], s4[8], s5[8];
+                    tc_ld8(t0 + 0 * TN, s2);
+                    tc_ld8(t0 + 1 * TN, s3);
+                    tc_ld8(t0 + 2 * TN, s4);
+                    tc_ld8(t0 + 3 * TN, s5);
+                    tc_wait_ld();
+                    // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + tb);
+                    if (hifi)
+                        epi_units8_hifi(s2, s3, s4, s5, cst, ksd, hacc);
+                    else if (has_counts)
+                        epi_units8<true>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                    else
+                        epi_units8<false>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(c_empty + cs);
                 }
-                if (hifi)
-                    epi_units8_hifi(b2, b3, b4, b5, cst + 8, ksd, hacc);
-                else if (has_counts)
-                    epi_units8<true>(b2, b3, b4, b5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                else
-                    epi_units8<false>(b2, b3, b4, b5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(c_empty + cs);
-                if (bt + 1 < bt1) tc_wait_ld();
             }
             const double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
