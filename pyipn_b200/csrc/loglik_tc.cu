@@ -24,7 +24,7 @@
 // TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
-// Warp roles: 0 = bulk-copy producer, 1 = tcgen05.cp + MMA issuer (one elected lane), 2..13 = epilogue.
+// Warp roles: 0..11 = epilogue, 12 = bulk-copy producer, 13 = tcgen05.cp + MMA issuer (one elected lane).
 #include "loglik_common.cuh"
 
 namespace ipn {
@@ -37,9 +37,14 @@ constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
 constexpr int EPI_WARPS = 12;      // 3 per TMEM lane quarter (and per SM sub-partition) rotating over 8-column groups
 constexpr int EPI_SLOTS = EPI_WARPS / 4;
-constexpr int GROUPS = TN / 8;     // 8-column groups per tile
+constexpr int GCOLS = 16;          // columns per epilogue work unit (two batches of 8)
+constexpr int GROUPS = TN / GCOLS; // work units per tile and lane quarter
 constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, group) and tile
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
+// The warp scheduler favours the highest warp id among eligible warps: the two light but latency-critical roles
+// get the top ids so the epilogue warps sharing their sub-partitions cannot starve them.
+constexpr int PRODUCER_WARP = EPI_WARPS;      // 12
+constexpr int MMA_WARP = EPI_WARPS + 1;       // 13
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
 constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
@@ -62,6 +67,8 @@ struct TcParams {
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
     const int* flags;         // [0] = #bins with counts, [1] = 1: fp64 epilogue (bright data)
+    int skip_mma;             // experiment switch (IPN_TC_SKIP_MMA): issue one MMA per tile only -> exposes the epilogue-bound period
+    int skip_math;            // experiment switch (IPN_TC_SKIP_MATH): epilogue only drains TMEM -> exposes the MMA-bound period
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
 };
 
@@ -309,6 +316,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     __trap();
 }
+// Polling with back-off for the producer: it runs 2-4 stages ahead, so wake-up latency is irrelevant, while a
+// tight try_wait loop would steal issue slots from the epilogue warps of its sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(256);
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
     if (!on) {
         mbar_wait(bar, parity);
@@ -498,7 +525,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -511,7 +538,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     const int items_per_draw = p.nchunk * p.n_dt;
     const int64_t n_items = (int64_t)p.Sb * items_per_draw;
 
-    if (warp == 0) {
+    if (warp == PRODUCER_WARP) {
         // ===== producer: bulk copies global -> shared, completion on the *_full barriers =====
         if (lane == 0) {
             uint32_t tile_seq = 0, item_seq = 0;
@@ -521,7 +548,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 const int sl = (int)(item / items_per_draw);
                 const int rem = (int)(item - (int64_t)sl * items_per_draw);
                 const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
-                mbar_wait(a_empty, (item_seq & 1) ^ 1);  // staging buffer copied into TMEM
+                mbar_wait_relaxed(a_empty, (item_seq & 1) ^ 1);  // staging buffer copied into TMEM
                 mbar_expect_tx(a_full, p.a_bytes);
                 bulk_g2s(sA, p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes, p.a_bytes, a_full);
                 const int bt0 = chunk * p.tiles_per_chunk;
@@ -529,11 +556,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                     const uint8_t* img = p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.img_bytes;
                     const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
-                    mbar_wait_timed(b_empty + st, ph ^ 1, w_be, dbg);  // released by the MMA commit
+                    mbar_wait_relaxed(b_empty + st, ph ^ 1);  // released by the MMA commit
                     mbar_expect_tx(b_full + st, p.b_dig);
                     bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + st);
                     const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                    mbar_wait_timed(c_empty + cs, cph ^ 1, w_ce, dbg);  // released by the epilogue warps
+                    mbar_wait_relaxed(c_empty + cs, cph ^ 1);  // released by the epilogue warps
                     mbar_expect_tx(c_full + cs, CONST_BYTES);
                     bulk_g2s(sC0 + (size_t)cs * CONST_BYTES, img + p.b_dig, CONST_BYTES, c_full + cs);
                 }
@@ -543,7 +570,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 p.dbg[blockIdx.x * 8 + 1] = w_ce;
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
         // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 32, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -588,6 +615,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     // accumulate into DIFFERENT level accumulators (no back-to-back read-modify-write of one tile).
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
+                        if (p.skip_mma && ks > 0) break;
 #pragma unroll
                         for (int pp = 0; pp < PP; ++pp) {
 #pragma unroll
@@ -622,7 +650,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         // (global group index mod 3), so at any time they sit in different phases (barrier wait / TMEM load / math)
         // and cover one another's latencies; every (quarter, group) arrives once per tile on t_empty / c_empty.
         const int quarter = warp & 3;        // TMEM lanes this warp may read
-        const int slot = (warp - 2) >> 2;    // 0..2
+        const int slot = warp >> 2;          // 0..2
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
         unsigned long long w_cf = 0, w_tf = 0;
@@ -653,24 +681,34 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
                 for (; cg < GROUPS; cg += EPI_SLOTS) {
-                    const float4* cst = cbase + cg * 8;
-                    const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * 8;
-                    int s2[8], s3[8], s4[8], s5[8];
+                    const float4* cst = cbase + cg * GCOLS;
+                    const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
+                    int s2[8], s3[8], s4[8], s5[8], r2[8], r3[8], r4[8], r5[8];
                     tc_ld8(t0 + 0 * TN, s2);
                     tc_ld8(t0 + 1 * TN, s3);
                     tc_ld8(t0 + 2 * TN, s4);
                     tc_ld8(t0 + 3 * TN, s5);
+                    tc_ld8(t0 + 0 * TN + 8, r2);
+                    tc_ld8(t0 + 1 * TN + 8, r3);
+                    tc_ld8(t0 + 2 * TN + 8, r4);
+                    tc_ld8(t0 + 3 * TN + 8, r5);
                     tc_wait_ld();
                     // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + tb);
-                    if (hifi)
+                    if (p.skip_math) {
+                        slo += __int_as_float(s2[0] ^ s3[1] ^ s4[2] ^ s5[3] ^ r2[0] ^ r3[1] ^ r4[2] ^ r5[3]) * 0.0f;
+                    } else if (hifi) {
                         epi_units8_hifi(s2, s3, s4, s5, cst, ksd, hacc);
-                    else if (has_counts)
+                        epi_units8_hifi(r2, r3, r4, r5, cst + 8, ksd, hacc);
+                    } else if (has_counts) {
                         epi_units8<true>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                    else
+                        epi_units8<true>(r2, r3, r4, r5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                    } else {
                         epi_units8<false>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                        epi_units8<false>(r2, r3, r4, r5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(c_empty + cs);
                 }
@@ -679,14 +717,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
         }
-        if (dbg && warp == 2 && lane == 0) {
+        if (dbg && warp == 0 && lane == 0) {
             p.dbg[blockIdx.x * 8 + 5] = w_cf;
             p.dbg[blockIdx.x * 8 + 6] = w_tf;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
@@ -777,6 +815,8 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
             p.flags = d_nnz;
+            p.skip_math = getenv("IPN_TC_SKIP_MATH") != nullptr;
+            p.skip_mma = getenv("IPN_TC_SKIP_MMA") != nullptr;
             p.dbg = nullptr;
             const bool want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
             if (want_dbg) {
