@@ -110,6 +110,17 @@ int ipn_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64_t 
 int ipn_poisson_counts_dev(ipn_ctx* ctx, int64_t T, const double* d_exposure, int64_t S, const double* d_rates,
                            const double* d_bkg, uint64_t seed, int64_t* d_out);
 
+/* ---- photon arrival times by thinning (next-row N2) ---------------------------------------------------
+ * replaces  source_poisson_generator / background_poisson_generator  pyipn/possion_gen.py:159-242 with the pulse shape
+ * of :9-62 (sum of up to 8 Norris pulses K exp(2 sqrt(tr/td)) exp(-tr/(t-ts) - (t-ts)/td)) over a linear background
+ * rate bkg_intercept + bkg_slope t (pass n_pulses = 0 for the background generator, 0/0 for a pure source).
+ * out_times receives tstart followed by the sorted accepted times (the reference emits tstart itself first);
+ * *out_count is the number written (or needed, if the call fails because capacity is too small).  Counter-based
+ * Philox streams keyed by (seed, candidate index): the same point process as the reference, not the same draws. */
+int ipn_thinning_events(ipn_ctx* ctx, double tstart, double tstop, int64_t n_pulses, const double* K,
+                        const double* t_start, const double* t_rise, const double* t_decay, double bkg_slope,
+                        double bkg_intercept, uint64_t seed, int64_t capacity, double* out_times, int64_t* out_count);
+
 /* ---- event binning (next-row N3) ------------------------------------------------------------------------
  * replaces  LightCurve.get_binned_light_curve  pyipn/lightcurve.py:24-47 (np.arange edges + np.histogram):
  * the caller passes n_edges = len(np.arange(tstart, tstop, dt)) and dt = edges[1] - edges[0] (numpy fills a float arange

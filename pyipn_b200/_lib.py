@@ -31,7 +31,7 @@ EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
     "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
-    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
+    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
 )
 
 
@@ -86,6 +86,8 @@ def load_library():
         pc_args = [_p, _i64, _p, _i64, _p, _p, C.c_uint64, _p]
         lib.ipn_poisson_counts.argtypes = pc_args
         lib.ipn_poisson_counts_dev.argtypes = pc_args
+        lib.ipn_thinning_events.argtypes = [_p, C.c_double, C.c_double, _i64, _p, _p, _p, _p, C.c_double, C.c_double, C.c_uint64,
+                                            _i64, _p, C.POINTER(_i64)]
         lib.ipn_bin_events.argtypes = [_p, _i64, _p, C.c_double, C.c_double, _i64, _p]
         lib.ipn_bin_events_dev.argtypes = [_p, _i64, _p, C.c_double, C.c_double, _i64, _p]
         lib.ipn_correlate.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_double, C.c_double,
@@ -236,6 +238,27 @@ class Context:
             self._h, D, _ptr(nbins), Tmax, _ptr(time), _ptr(exposure), _ptr(counts), _ptr(sc_pos), P, _ptr(ghat), S, J,
             _ptr(omega), _ptr(a), _ptr(b), _ptr(amp), _ptr(bkg), _ptr(out)))
         return out
+
+    def thinning_events(self, tstart, tstop, K=(), t_start=(), t_rise=(), t_decay=(), bkg_slope=0.0, bkg_intercept=0.0,
+                        seed=1234):
+        """Arrival times on [tstart, tstop] of sum-of-Norris-pulses + linear background (possion_gen.py:159-242)."""
+        K, t_start, t_rise, t_decay = (_f64(np.atleast_1d(x)).ravel() for x in (K, t_start, t_rise, t_decay))
+        n = K.size
+        if not (t_start.size == t_rise.size == t_decay.size == n):
+            raise ValueError("pulse parameter arrays must have the same length")
+        # capacity from the integral bound fmax*(span) is only known on the device: start generous, grow on demand
+        cap = 1 << 16
+        cnt = _i64(0)
+        while True:
+            out = np.empty(cap, dtype=np.float64)
+            rc = self._lib.ipn_thinning_events(self._h, float(tstart), float(tstop), n, _ptr(K), _ptr(t_start), _ptr(t_rise),
+                                               _ptr(t_decay), float(bkg_slope), float(bkg_intercept),
+                                               C.c_uint64(int(seed) & (2**64 - 1)), cap, _ptr(out), C.byref(cnt))
+            if rc == IPN_ERR_INVALID_ARGUMENT and cnt.value > cap:
+                cap = int(cnt.value) + 16
+                continue
+            _check(self._lib, rc)
+            return out[: cnt.value].copy()
 
     def bin_events(self, times, tstart, tstop, dt):
         """(rate, edges, counts) with the semantics of LightCurve.get_binned_light_curve (lightcurve.py:24-47)."""

@@ -69,3 +69,17 @@ def background_poisson_generator(tstart, tstop, slope, intercept, seed=1234):
     grid = np.linspace(tstart, tstop + 1.0, 1000)
     fmax = (intercept + slope * grid).max()
     return _thin(rs, tstart, tstop, fmax, lambda t: intercept + slope * t)
+
+
+def source_poisson_generator_gpu(tstart, tstop, K, p_start, t_rise, t_decay, seed=1234):
+    """Device version of :func:`source_poisson_generator` (``ipn_thinning_events``): same point process, Philox stream."""
+    from ._lib import default_context
+
+    return default_context().thinning_events(tstart, tstop, K, p_start, t_rise, t_decay, 0.0, 0.0, seed)
+
+
+def background_poisson_generator_gpu(tstart, tstop, slope, intercept, seed=1234):
+    """Device version of :func:`background_poisson_generator`."""
+    from ._lib import default_context
+
+    return default_context().thinning_events(tstart, tstop, (), (), (), (), slope, intercept, seed)
