@@ -300,6 +300,14 @@ static int check_grid_host_values(int64_t T, const double* time, const double* e
     }
     IPN_REQUIRE(all_finite(omega, S * J) && all_finite(a, S * J) && all_finite(b, S * J),
                 "omega/a/b contain a non-finite value");
+    for (int64_t i = 0; i < S * J; ++i) {
+        // |a_j|, |b_j| are log-intensity amplitudes (the Stan model has them ~ N(0,1)/sqrt(k)); beyond e^40 per term the
+        // 8-bit digit planes of the delay table would saturate and the fp32 exponent is meaningless anyway
+        if (a[i] * a[i] + b[i] * b[i] > 1600.0) {
+            set_error("draw %lld: |a_j|, |b_j| of feature %lld exceed 40 (log-intensity amplitude)", (long long)(i / J), (long long)(i % J));
+            return IPN_ERR_UNSUPPORTED;
+        }
+    }
     for (int64_t s = 0; s < S; ++s) {
         IPN_REQUIRE(isfinite(bkg[s]) && bkg[s] > 0.0, "bkg[%lld] must be finite and > 0", (long long)s);
         IPN_REQUIRE(isfinite(amp[s]) && amp[s] >= 0.0, "amp[%lld] must be finite and >= 0", (long long)s);

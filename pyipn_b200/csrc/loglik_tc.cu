@@ -56,6 +56,8 @@ constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224)
 struct TcDraw {
     float ks;     // kappa = 2^-12 / sigma
     float sigma;  // power of two
+    int hifi;     // 1: fp64 epilogue for this draw
+    int pad;
 };
 
 struct TcParams {
@@ -66,7 +68,7 @@ struct TcParams {
     int Sb, n_dt, n_bt, nchunk, tiles_per_chunk, ksteps;
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
-    const int* flags;         // [0] = #bins with counts, [1] = 1: fp64 epilogue (bright data)
+    const int* flags;         // [0] = #bins with counts, [1] = epilogue mode option, [2..3] = sum n_i^2 (double)
     int skip_mma;             // experiment switch (IPN_TC_SKIP_MMA): issue one MMA per tile only -> exposes the epilogue-bound period
     int skip_math;            // experiment switch (IPN_TC_SKIP_MATH): epilogue only drains TMEM -> exposes the MMA-bound period
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
@@ -93,7 +95,8 @@ __device__ __forceinline__ void split_digits4(int q, int8_t& d1, int8_t& d2, int
 
 // sigma / kappa of every draw: sigma = largest power of two with sigma*max|W| <= 1 and sigma*|c| <= n_crows
 __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const double* __restrict__ a,
-                               const double* __restrict__ b, const DrawConst* __restrict__ dc, TcDraw* __restrict__ td) {
+                               const double* __restrict__ b, const DrawConst* __restrict__ dc, const int* __restrict__ flags,
+                               TcDraw* __restrict__ td) {
     const int sl = blockIdx.x * blockDim.x + threadIdx.x;
     if (sl >= Sb) return;
     const int64_t s = S0 + sl;
@@ -109,6 +112,13 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     TcDraw t;
     t.sigma = (float)ldexp(1.0, e);
     t.ks = (float)ldexp(1.0, -12 - e);
+    // fp32 epilogue error model: rms |dll| ~ 3.5e-8 ln2 y sqrt(sum n_i^2) with y ~ max(1, log2(A/B)) the size of
+    // log2(1+u).  Above ~5e-5 nats predicted (bright, coarsely binned data, or a source far above the background) the
+    // draw is evaluated with the fp64 epilogue.  flags[1]: 0 auto, 1 always, 2 never.
+    const double sumsq = *reinterpret_cast<const double*>(flags + 2);
+    const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
+    t.hifi = flags[1] == 1 ? 1 : (flags[1] == 2 ? 0 : (ysc * ysc * sumsq > 4.0e6 ? 1 : 0));
+    t.pad = 0;
     td[sl] = t;
 }
 
@@ -138,8 +148,9 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
                 const double w = omega[s * J + j], aj = a[s * J + j], bj = b[s * J + j];
                 double sn, cn;
                 sincos(w * dl, &sn, &cn);
-                q0 = (int)llrint(kLog2e * (aj * cn - bj * sn) * sigma * 1073741824.0);
-                q1 = (int)llrint(kLog2e * (aj * sn + bj * cn) * sigma * 1073741824.0);
+                // saturate instead of wrapping if a caller of the _dev entry point passes amplitudes beyond the supported range
+                q0 = (int)llrint(fmin(fmax(kLog2e * (aj * cn - bj * sn) * sigma, -1.0), 1.0) * 1073741824.0);
+                q1 = (int)llrint(fmin(fmax(kLog2e * (aj * sn + bj * cn) * sigma, -1.0), 1.0) * 1073741824.0);
             } else if (isfinite(cs)) {
                 // additive constant c spread exactly over the ncrow constant rows
                 const long long tot = llrint(cs * sigma * 1073741824.0);
@@ -195,9 +206,8 @@ __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t*
         s_total = t;
         s_carry = 0;
         n_nz_out[0] = t;
-        // fp32 epilogue error model: rms |dll| ~ 1.5e-7 sqrt(sum n_i^2).  Above ~1.5e-4 nats predicted
-        // (bright, coarsely binned data) the kernel switches to the fp64 epilogue.  hifi_mode: 0 auto, 1 on, 2 off.
-        n_nz_out[1] = hifi_mode == 1 ? 1 : (hifi_mode == 2 ? 0 : (q > 1.0e6 ? 1 : 0));
+        n_nz_out[1] = hifi_mode;
+        *reinterpret_cast<double*>(n_nz_out + 2) = q;  // sum n_i^2, read by tc_draw_kernel for the per-draw epilogue choice
     }
     __syncthreads();
     const int total = s_total;
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             double hacc = 0.0;
-            const bool hifi = p.flags[1] != 0;
+            const bool hifi = p.td[sl].hifi != 0;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
@@ -760,13 +770,11 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     if ((rc = ctx->misc.ensure((size_t)Sbatch * p_per_draw))) return rc;
     if ((rc = ctx->accum.ensure((size_t)Sbatch * Gpad * sizeof(double)))) return rc;
     if ((rc = ctx->tcdraw.ensure((size_t)Sbatch * sizeof(TcDraw)))) return rc;
-    if ((rc = ctx->perm.ensure((size_t)(T + 1) * sizeof(int) + 16))) return rc;
-    int* d_nnz = ctx->perm.as<int>();
-    int* d_perm = d_nnz + 4;
-    if (T > 0) {
-        tc_perm_kernel<<<1, 1024, 0, ctx->stream>>>(T, counts, d_perm, d_nnz, ctx->hifi_mode);
-        ctx->launches += 1;
-    }
+    if ((rc = ctx->perm.ensure((size_t)(T + 1) * sizeof(int) + 64))) return rc;
+    int* d_nnz = ctx->perm.as<int>();  // [0] n_nz, [1] mode, [2..3] sum n^2 as double (8-byte aligned)
+    int* d_perm = d_nnz + 8;
+    tc_perm_kernel<<<1, 1024, 0, ctx->stream>>>(T, counts, d_perm, d_nnz, ctx->hifi_mode);  // T == 0: only writes the flags
+    ctx->launches += 1;
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
     uint8_t* d_P = ctx->misc.as<uint8_t>();
     double* d_R = ctx->accum.as<double>();
@@ -787,7 +795,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
         IPN_CUDA_CHECK(cudaMemsetAsync(d_R, 0, (size_t)Sb * Gpad * sizeof(double), ctx->stream));
-        tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_td);
+        tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_nnz, d_td);
         tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
                                                                             n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
