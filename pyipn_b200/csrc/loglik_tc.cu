@@ -113,11 +113,11 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     t.sigma = (float)ldexp(1.0, e);
     t.ks = (float)ldexp(1.0, -12 - e);
     // fp32 epilogue error model: rms |dll| ~ 3.5e-8 ln2 y sqrt(sum n_i^2) with y ~ max(1, log2(A/B)) the size of
-    // log2(1+u).  Above ~5e-5 nats predicted (bright, coarsely binned data, or a source far above the background) the
+    // log2(1+u).  Above ~2.5e-5 nats rms predicted (bright, coarsely binned data, or a source far above the background) the
     // draw is evaluated with the fp64 epilogue.  flags[1]: 0 auto, 1 always, 2 never.
     const double sumsq = *reinterpret_cast<const double*>(flags + 2);
     const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
-    t.hifi = flags[1] == 1 ? 1 : (flags[1] == 2 ? 0 : (ysc * ysc * sumsq > 4.0e6 ? 1 : 0));
+    t.hifi = flags[1] == 1 ? 1 : (flags[1] == 2 ? 0 : (ysc * ysc * sumsq > 1.0e6 ? 1 : 0));
     t.pad = 0;
     td[sl] = t;
 }
