@@ -170,9 +170,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace = (lambda m: print("[bench] " + m, file=sys.stderr, flush=True)) if os.environ.get("IPN_BENCH_TRACE") else (lambda m: None)
     for _ in range(a.warmup):
         step_resident()
         ctx.synchronize()
+        trace("warm-up step done")
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
@@ -187,8 +189,10 @@ def main():
         m, n = ctx.last_main_kernel
         main_ms += m
         main_launches += n
+        trace("timed step done")
     ev1.record()
     barrier()
+    trace("timed region closed")
     clocks = sampler.stop() if sampler else None
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
@@ -214,6 +218,7 @@ def main():
 
     step_e2e()
     barrier()
+    trace("e2e warm-up done")
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_e2e()

@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libipn_b200.so")
+LIB_PATH = os.environ.get("IPN_B200_LIB") or os.path.join(HERE, "libipn_b200.so")  # IPN_B200_LIB: explicit path to the library
 
 IPN_OK = 0
 IPN_ERR_INVALID_ARGUMENT = -1

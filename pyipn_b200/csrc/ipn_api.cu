@@ -10,11 +10,42 @@ namespace ipn {
 
 static thread_local char g_err[1024] = "";
 
+// Record a kernel writes (through a host-mapped pointer) just before it traps on a barrier time-out; host memory stays
+// readable after the context has died with "unspecified launch failure", so the message can say which wait it was.
+static volatile int* g_trap_host = nullptr;
+
+int* trap_record_device_ptr() {
+    static int* dev = nullptr;
+    if (!dev) {
+        int* host = nullptr;
+        if (cudaHostAlloc(&host, 32 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        memset(host, 0, 32 * sizeof(int));
+        if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            dev = nullptr;
+            return nullptr;
+        }
+        g_trap_host = host;
+    }
+    return dev;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    int n = vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    if (g_trap_host && g_trap_host[0] != 0 && n >= 0 && n < (int)sizeof(g_err) - 1)
+    {
+        n += snprintf(g_err + n, sizeof(g_err) - n, " [kernel barrier time-out: wait id %d, block %d, warp %d, parity %d, sequence %d; last wait (id:sequence) per warp:",
+                      g_trap_host[0], g_trap_host[1], g_trap_host[2], g_trap_host[3], g_trap_host[4]);
+        for (int w = 0; w < 16 && n < (int)sizeof(g_err) - 24; ++w)
+            n += snprintf(g_err + n, sizeof(g_err) - n, " %d:%d", (int)((unsigned)g_trap_host[8 + w] >> 24), g_trap_host[8 + w] & 0xFFFFFF);
+        if (n < (int)sizeof(g_err) - 2) snprintf(g_err + n, sizeof(g_err) - n, "]");
+    }
 }
 
 int Scratch::ensure(size_t bytes) {

@@ -11,6 +11,7 @@
 namespace ipn {
 
 void set_error(const char* fmt, ...);
+int* trap_record_device_ptr();  // host-mapped int[16]; nullptr if it cannot be allocated
 
 #define IPN_CUDA_CHECK(expr)                                                                      \
     do {                                                                                          \

@@ -24,7 +24,8 @@
 // TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
-// Warp roles: 0..11 = epilogue, 12 = bulk-copy producer, 13 = tcgen05.cp + MMA issuer (one elected lane).
+// Warp roles: 0..11 = epilogue, 12 = bulk-copy producer, 13 / 14 = MMA issuers of the even / odd tiles (13 also does the
+// tcgen05.cp of the W digits).
 #include "loglik_common.cuh"
 
 namespace ipn {
@@ -40,15 +41,22 @@ constexpr int EPI_SLOTS = EPI_WARPS / 4;
 constexpr int GCOLS = 16;          // columns per epilogue work unit (two batches of 8)
 constexpr int GROUPS = TN / GCOLS; // work units per tile and lane quarter
 constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, group) and tile
-constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
+constexpr int NTHREADS = (3 + EPI_WARPS) * 32;
 // The warp scheduler favours the highest warp id among eligible warps: the two light but latency-critical roles
 // get the top ids so the epilogue warps sharing their sub-partitions cannot starve them.
 constexpr int PRODUCER_WARP = EPI_WARPS;      // 12
-constexpr int MMA_WARP = EPI_WARPS + 1;       // 13
+constexpr int MMA_WARP = EPI_WARPS + 1;       // 13: issues the even tiles (accumulator buffer 0) and the TMEM copies of W
+constexpr int MMA_WARP2 = EPI_WARPS + 2;      // 14: issues the odd tiles (accumulator buffer 1) from another sub-partition
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
 constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
-constexpr int NCST = 8;                    // depth of the shared-memory ring of those constant blocks
+// A parity wait on an mbarrier is only sound if the waiter sees EVERY phase of that barrier (it cannot tell "two phases
+// away" from "done").  A warp of epilogue slot s owns groups with (2 tile + g) % 3 == s, so it skips every third tile; with
+// two MMA issuers tiles may also complete out of order.  Hence every barrier an epilogue warp waits on is indexed by
+// tile % (a multiple of 3): all uses of one barrier then belong to the same warps, and the others never look at it.
+constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks (multiple of 3)
+constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6 (2 TMEM buffers x ownership period 3)
+static_assert(NCST % EPI_SLOTS == 0 && NTF % EPI_SLOTS == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
 constexpr int NBST = 4;                    // depth of the Phi digit-plane ring
 constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
 }  // namespace tc
@@ -69,6 +77,8 @@ struct TcParams {
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
     const int* flags;         // [0] = #bins with counts, [1] = epilogue mode option, [2..3] = sum n_i^2 (double)
+    int one_issuer;           // experiment switch (IPN_TC_ONE_ISSUER): warp 13 issues every tile, warp 14 only takes part in the hand-shakes
+    int epi_delay;            // test hook (IPN_TC_EPI_DELAY, cycles): stall every epilogue unit -> protocol must survive a slow consumer
     int skip_mma;             // experiment switch (IPN_TC_SKIP_MMA): issue one MMA per tile only -> exposes the epilogue-bound period
     int skip_math;            // experiment switch (IPN_TC_SKIP_MATH): epilogue only drains TMEM -> exposes the MMA-bound period
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
@@ -307,10 +317,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Where a timed-out wait leaves its identity before trapping (host-mapped, see trap_record_device_ptr()).
+__device__ int* g_trap_record = nullptr;
+enum WaitId { W_A_FULL = 1, W_A_EMPTY, W_A_TMEM_FULL, W_A_TMEM_FREE, W_B_FULL, W_B_EMPTY, W_C_FULL, W_C_EMPTY, W_T_FULL, W_T_EMPTY };
+
+__device__ __noinline__ void mbar_timeout(int id, uint32_t parity, uint32_t seq, const volatile uint32_t* prog) {
+    int* r = g_trap_record;
+    if (r && atomicCAS(r, 0, id) == 0) {
+        r[1] = (int)blockIdx.x;
+        r[2] = (int)(threadIdx.x >> 5);
+        r[3] = (int)parity;
+        r[4] = (int)seq;
+        for (int w = 0; w < 16; ++w) r[8 + w] = (int)prog[w];  // what every warp of the CTA was last waiting for
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id, uint32_t seq, volatile uint32_t* prog) {
     // bounded spin: a protocol bug must surface as a launch failure (trap), never as a hung GPU
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        if (spin == 1) prog[threadIdx.x >> 5] = ((uint32_t)id << 24) | (seq & 0xFFFFFFu);  // not ready at once: note what we wait for
         uint32_t done;
         asm volatile(
             "{\n\t"
@@ -324,12 +352,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) return;
     }
-    __trap();
+    mbar_timeout(id, parity, seq, prog);
 }
 // Polling with back-off for the producer: it runs 2-4 stages ahead, so wake-up latency is irrelevant, while a
 // tight try_wait loop would steal issue slots from the epilogue warps of its sub-partition.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+template <int SLEEP_NS = 256>
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int id, uint32_t seq, volatile uint32_t* prog) {
+    prog[threadIdx.x >> 5] = ((uint32_t)id << 24) | (seq & 0xFFFFFFu);
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t done;
         asm volatile(
@@ -342,17 +373,18 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        __nanosleep(256);
+        __nanosleep(SLEEP_NS);
     }
-    __trap();
+    mbar_timeout(id, parity, seq, prog);
 }
-__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+// Wait with optional cycle accounting (IPN_TC_DEBUG)
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on, int id, uint32_t seq, volatile uint32_t* prog) {
     if (!on) {
-        mbar_wait(bar, parity);
+        mbar_wait(bar, parity, id, seq, prog);
         return;
     }
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait(bar, parity, id, seq, prog);
     acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -495,7 +527,9 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // ------------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------------
-template <int KSTEPS>
+// HIFI = true instantiation: only the draws flagged for the fp64 epilogue (every role skips the others' items), so the
+// common fp32 instantiation carries no fp64 exp2/log1p code in its instruction-cache footprint.
+template <int KSTEPS, bool HIFI>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -505,13 +539,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* bars = reinterpret_cast<uint64_t*>(sC0 + NCST * CONST_BYTES);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* t_full = bars + 2;             // [2]
-    uint64_t* t_empty = bars + 4;            // [2]
-    uint64_t* b_full = bars + 6;             // [NBST]
+    uint64_t* t_empty = bars + 2;            // [2]
+    uint64_t* t_full = bars + 4;             // [NTF]
+    uint64_t* b_full = t_full + NTF;         // [NBST]
     uint64_t* b_empty = b_full + NBST;       // [NBST]
     uint64_t* c_full = b_empty + NBST;       // [NCST]
     uint64_t* c_empty = c_full + NCST;       // [NCST]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + NCST);
+    uint64_t* a_tmem_full = c_empty + NCST;  // W digits of the current item are in tensor memory (issuer 0 -> issuer 1)
+    uint64_t* a_tmem_free = a_tmem_full + 1; // both issuers' MMAs of the item have finished reading them (-> issuer 0)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_tmem_free + 1);
+    volatile uint32_t* prog = tmem_slot + 4;  // [16] last wait of every warp (time-out diagnostics)
 
     // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
@@ -521,10 +558,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, EPI_ARRIVALS);
-        }
+        mbar_init(a_tmem_full, 1);
+        mbar_init(a_tmem_free, 2);
+        for (int i = 0; i < 2; ++i) mbar_init(t_empty + i, EPI_ARRIVALS);
+        for (int i = 0; i < NTF; ++i) mbar_init(t_full + i, 1);
         for (int i = 0; i < NBST; ++i) {
             mbar_init(b_full + i, 1);
             mbar_init(b_empty + i, 1);
@@ -556,9 +593,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const bool dbg = p.dbg != nullptr;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int sl = (int)(item / items_per_draw);
+                if ((p.td[sl].hifi != 0) != HIFI) {
+                    --item_seq;  // not this instantiation's draw: the item does not exist for any role
+                    continue;
+                }
                 const int rem = (int)(item - (int64_t)sl * items_per_draw);
                 const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
-                mbar_wait_relaxed(a_empty, (item_seq & 1) ^ 1);  // staging buffer copied into TMEM
+                mbar_wait_relaxed(a_empty, (item_seq & 1) ^ 1, W_A_EMPTY, item_seq, prog);  // staging buffer copied into TMEM
                 mbar_expect_tx(a_full, p.a_bytes);
                 bulk_g2s(sA, p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes, p.a_bytes, a_full);
                 const int bt0 = chunk * p.tiles_per_chunk;
@@ -566,11 +607,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                     const uint8_t* img = p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.img_bytes;
                     const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
-                    mbar_wait_relaxed(b_empty + st, ph ^ 1);  // released by the MMA commit
+                    mbar_wait_relaxed(b_empty + st, ph ^ 1, W_B_EMPTY, tile_seq, prog);  // released by the MMA commit
                     mbar_expect_tx(b_full + st, p.b_dig);
                     bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + st);
                     const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
-                    mbar_wait_relaxed(c_empty + cs, cph ^ 1);  // released by the epilogue warps
+                    mbar_wait_relaxed(c_empty + cs, cph ^ 1, W_C_EMPTY, tile_seq, prog);  // released by the epilogue warps
                     mbar_expect_tx(c_full + cs, CONST_BYTES);
                     bulk_g2s(sC0 + (size_t)cs * CONST_BYTES, img + p.b_dig, CONST_BYTES, c_full + cs);
                 }
@@ -580,8 +621,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 p.dbg[blockIdx.x * 8 + 1] = w_ce;
             }
         }
-    } else if (warp == MMA_WARP) {
-        // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
+    } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        // ===== MMA issuers: two warps on different sub-partitions, one per accumulator buffer (even / odd tiles) =====
+        // Measured: with the epilogue math running on its sub-partition a single issuing warp needs ~2200 cycles for the
+        // 63 MMAs of a tile (the tensor pipe needs 1000); two issuers halve that.  Each walks the whole (warp-uniform)
+        // schedule and one elected lane issues the tiles of its parity.
+        const uint32_t which = warp == MMA_WARP ? 0u : 1u;
         // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N = 32, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         constexpr uint32_t a_lbo = TM * 16, b_lbo = TN * 16;
@@ -594,29 +639,42 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = p.dbg != nullptr;
         const long long t_start = clock64();
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
+            if ((p.td[(int)(item / items_per_draw)].hifi != 0) != HIFI) {
+                --item_seq;
+                continue;
+            }
             const int rem = (int)(item % items_per_draw);
             const int chunk = rem / p.n_dt;
             const int bt0 = chunk * p.tiles_per_chunk;
             const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
-            mbar_wait_timed(a_full, item_seq & 1, w_af, dbg);
-            tc_fence_after();
-            if (elect_one()) {
-                // W digit planes: shared -> tensor memory, 8 columns (32 K-bytes x 128 lanes) per copy.  tcgen05.cp and
-                // tcgen05.mma execute in issue order, so these land after the previous item's MMAs have read TMEM.
+            if (which == 0) {
+                mbar_wait_timed(a_full, item_seq & 1, w_af, dbg, W_A_FULL, item_seq, prog);
+                mbar_wait(a_tmem_free, (item_seq & 1) ^ 1, W_A_TMEM_FREE, item_seq, prog);  // all MMAs of the previous item have read its W digits
+                tc_fence_after();
+                if (elect_one()) {
+                    // W digit planes: shared -> tensor memory, 8 columns (32 K-bytes x 128 lanes) per copy.  PTX orders
+                    // cp -> mma of one thread but not mma -> cp, hence the a_tmem_free hand-shake above (a pipeline drain
+                    // per item, i.e. per >= 16 tiles).
 #pragma unroll
-                for (int q = 0; q < PW; ++q)
+                    for (int q = 0; q < PW; ++q)
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks)
-                        tc_cp_128x256b(tmem_base + (q * KSTEPS + ks) * 8,
-                                       a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4)));
-                tc_commit(a_empty);  // staging buffer free once the copies have completed
+                        for (int ks = 0; ks < KSTEPS; ++ks)
+                            tc_cp_128x256b(tmem_base + (q * KSTEPS + ks) * 8,
+                                           a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4)));
+                    tc_commit(a_empty);      // staging buffer free once the copies have completed
+                    tc_commit(a_tmem_full);  // ... and issuer 1 may start on this item
+                }
+                __syncwarp();
+            } else {
+                mbar_wait(a_tmem_full, item_seq & 1, W_A_TMEM_FULL, item_seq, prog);
+                tc_fence_after();
             }
-            __syncwarp();
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                if ((p.one_issuer ? 0u : (tile_seq & 1)) != which) continue;
                 const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
-                mbar_wait_timed(b_full + st, ph, w_bf, dbg);
-                mbar_wait_timed(t_empty + tb, tph ^ 1, w_te, dbg);
+                mbar_wait_timed(b_full + st, ph, w_bf, dbg, W_B_FULL, tile_seq, prog);
+                mbar_wait_timed(t_empty + tb, tph ^ 1, w_te, dbg, W_T_EMPTY, tile_seq, prog);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + ACC_COL0 + tb * (NLEV * TN);
                 const uint32_t b_base = b_base0 + st * (p.b_dig >> 4);
@@ -643,12 +701,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                         }
                     }
                     tc_commit(b_empty + st);  // operands of this stage consumed
-                    tc_commit(t_full + tb);   // accumulators of this buffer complete
+                    tc_commit(t_full + tile_seq % NTF);  // accumulators of this tile complete
                 }
                 __syncwarp();
             }
+            if (elect_one()) tc_commit(a_tmem_free);  // arrives when this issuer's MMAs of the item have completed
+            __syncwarp();
         }
-        if (dbg && lane == 0) {
+        if (dbg && lane == 0 && which == 0) {
             p.dbg[blockIdx.x * 8 + 2] = w_af;
             p.dbg[blockIdx.x * 8 + 3] = w_bf;
             p.dbg[blockIdx.x * 8 + 4] = w_te;
@@ -667,6 +727,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = p.dbg != nullptr;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int sl = (int)(item / items_per_draw);
+            if ((p.td[sl].hifi != 0) != HIFI) continue;
             const int rem = (int)(item - (int64_t)sl * items_per_draw);
             const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
             const int bt0 = chunk * p.tiles_per_chunk;
@@ -677,16 +738,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             double hacc = 0.0;
-            const bool hifi = p.td[sl].hifi != 0;
+            constexpr bool hifi = HIFI;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
                 // groups of this tile that belong to this warp: (tile_seq * GROUPS + cg) % EPI_SLOTS == slot
                 int cg = (int)((slot + EPI_SLOTS - (tile_seq * GROUPS) % EPI_SLOTS) % EPI_SLOTS);
-                if (cg >= GROUPS) continue;
-                mbar_wait_timed(c_full + cs, cph, w_cf, dbg);  // the tile's Poisson constants are in shared memory
-                mbar_wait_timed(t_full + tb, tph, w_tf, dbg);
+                if (cg >= GROUPS) continue;  // not this warp's tile; it never touches that tile's barriers (see NTF)
+                mbar_wait_timed(c_full + cs, cph, w_cf, dbg, W_C_FULL, tile_seq, prog);  // the tile's Poisson constants are in shared memory
+                mbar_wait_timed(t_full + tile_seq % NTF, (tile_seq / NTF) & 1, w_tf, dbg, W_T_FULL, tile_seq, prog);
                 tc_fence_after();
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
@@ -707,7 +768,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + tb);
-                    if (p.skip_math) {
+                    if (p.epi_delay) {
+                        const long long d0 = clock64();
+                        while (clock64() - d0 < (long long)p.epi_delay * (1 + ((warp * 7 + tile_seq) & 3))) {}
+                    }
+                    if (p.skip_math == 1 || (p.skip_math == 2 && quarter == (MMA_WARP & 3))) {
                         slo += __int_as_float(s2[0] ^ s3[1] ^ s4[2] ^ s5[3] ^ r2[0] ^ r3[1] ^ r4[2] ^ r5[3]) * 0.0f;
                     } else if (hifi) {
                         epi_units8_hifi(s2, s3, s4, s5, cst, ksd, hacc);
@@ -756,7 +821,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
-    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (6 + 2 * NBST + 2 * NCST) * 8 + 16;
+    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (6 + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 64;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -781,15 +846,18 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
     void (*kern)(const TcParams) = nullptr;
+    void (*kern_hifi)(const TcParams) = nullptr;
     switch (ksteps) {
-        case 1: kern = loglik_tc_kernel<1>; break;
-        case 2: kern = loglik_tc_kernel<2>; break;
-        case 3: kern = loglik_tc_kernel<3>; break;
-        case 4: kern = loglik_tc_kernel<4>; break;
-        case 5: kern = loglik_tc_kernel<5>; break;
-        case 6: kern = loglik_tc_kernel<6>; break;
-        default: kern = loglik_tc_kernel<7>; break;
+#define IPN_TC_CASE(K) case K: kern = loglik_tc_kernel<K, false>; kern_hifi = loglik_tc_kernel<K, true>; break;
+        IPN_TC_CASE(1) IPN_TC_CASE(2) IPN_TC_CASE(3) IPN_TC_CASE(4) IPN_TC_CASE(5) IPN_TC_CASE(6)
+        default: kern = loglik_tc_kernel<7, false>; kern_hifi = loglik_tc_kernel<7, true>; break;
+#undef IPN_TC_CASE
     }
+    {
+        int* trap = trap_record_device_ptr();
+        IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    IPN_CUDA_CHECK(cudaFuncSetAttribute(kern_hifi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IPN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
@@ -814,6 +882,11 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                 if (nchunk > max_chunks) nchunk = max_chunks;
                 if (nchunk < 1) nchunk = 1;
             }
+            // ... and when there are many tiles, so that an item lasts ~0.1 ms: the 32 delay tiles that share a chunk of Phi
+            // start up to one item apart (148 CTAs is not a multiple of 32), and the chunk must still be in L2 for the late
+            // ones (ncu: 600-tile items re-read half of Phi from HBM, 2.2x the minimum traffic)
+            const int max_tiles = getenv("IPN_TC_CHUNK_TILES") ? atoi(getenv("IPN_TC_CHUNK_TILES")) : 128;
+            if ((n_bt + nchunk - 1) / nchunk > max_tiles) nchunk = (n_bt + max_tiles - 1) / max_tiles;
             const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
             nchunk = (n_bt + tiles_per_chunk - 1) / tiles_per_chunk;
             TcParams p;
@@ -821,10 +894,13 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             p.Sb = Sb; p.n_dt = n_dt; p.n_bt = n_bt; p.nchunk = nchunk; p.tiles_per_chunk = tiles_per_chunk; p.ksteps = ksteps;
             p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_dig = b_dig; p.img_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
-            const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+            int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+            if (getenv("IPN_TC_GRID")) grid = (int)std::min<int64_t>(items, atoi(getenv("IPN_TC_GRID")));  // test hook: several CTA waves
             p.flags = d_nnz;
-            p.skip_math = getenv("IPN_TC_SKIP_MATH") != nullptr;
+            p.skip_math = getenv("IPN_TC_SKIP_MATH") ? atoi(getenv("IPN_TC_SKIP_MATH")) : 0;
             p.skip_mma = getenv("IPN_TC_SKIP_MMA") != nullptr;
+            p.epi_delay = getenv("IPN_TC_EPI_DELAY") ? atoi(getenv("IPN_TC_EPI_DELAY")) : 0;
+            p.one_issuer = getenv("IPN_TC_ONE_ISSUER") != nullptr;
             p.dbg = nullptr;
             const bool want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
             if (want_dbg) {
@@ -834,8 +910,9 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             }
             main_kernel_begin(ctx);
             kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
+            if (ctx->hifi_mode != 2) kern_hifi<<<grid, NTHREADS, smem, ctx->stream>>>(p);  // draws flagged for the fp64 epilogue
             main_kernel_end(ctx);
-            ctx->launches += 1;
+            ctx->launches += ctx->hifi_mode != 2 ? 2 : 1;
             IPN_CUDA_CHECK(cudaGetLastError());
             if (want_dbg) {
                 std::vector<unsigned long long> h((size_t)grid * 8);
