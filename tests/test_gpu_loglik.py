@@ -195,3 +195,47 @@ def test_sky_grid_vs_oracle(ctx):
     assert ll.shape == (48, 2)
     assert np.abs(ll - exp).max() < ATOL
     np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(exp, axis=0))
+
+
+@pytest.mark.parametrize("hook", [{"IPN_TC_GRID": "600"}, {"IPN_TC_GRID": "37"}, {"IPN_TC_EPI_DELAY": "20000"},
+                                  {"IPN_TC_CHUNK_TILES": "16"}, {"IPN_TC_ONE_ISSUER": "1"}])
+def test_tc_pipeline_schedule_independence(ctx, monkeypatch, hook):
+    """The tcgen05 kernel's result must not depend on how its warp roles are paced or its items are cut: several CTA
+    waves per SM, fewer CTAs than SMs, an artificially slow epilogue, tiny items, a single MMA issuer.  (A dead-lock in
+    the barrier protocol shows up here as a launch failure with the time-out record in the message.)"""
+    from pyipn_b200._lib import OPT_LOGLIK_IMPL
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=30_000, G=1024, S=6)
+    args = (w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    ctx.set_option(OPT_LOGLIK_IMPL, 2)
+    try:
+        base = ctx.loglik_delay_grid(*args)
+        for k, v in hook.items():
+            monkeypatch.setenv(k, v)
+        got = ctx.loglik_delay_grid(*args)
+    finally:
+        ctx.set_option(OPT_LOGLIK_IMPL, 0)
+    # same arithmetic per (delay, bin); only the order of the float64 partial sums changes
+    assert np.abs(got - base).max() < 1e-7
+    exp = orc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"][:1], w["a"][:1], w["b"][:1], w["amp"][:1],
+                                w["bkg"][:1], w["delays"][::64])
+    assert np.abs(got[::64, :1] - exp).max() < ATOL
+
+
+@pytest.mark.parametrize("hook", [{"IPN_TC_SKIP_MATH": "1"}, {"IPN_TC_SKIP_MATH": "2"}, {"IPN_TC_SKIP_MMA": "1"}])
+def test_tc_pipeline_survives_unbalanced_roles(ctx, monkeypatch, hook):
+    """Experiment switches that make one role much faster than the others (values are meaningless then): the hand-shakes
+    must still complete.  This is the regime in which a skipped barrier phase dead-locked the two-issuer kernel."""
+    from pyipn_b200._lib import OPT_LOGLIK_IMPL
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=100_000, G=2048, S=8)
+    for k, v in hook.items():
+        monkeypatch.setenv(k, v)
+    ctx.set_option(OPT_LOGLIK_IMPL, 2)
+    try:
+        ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    finally:
+        ctx.set_option(OPT_LOGLIK_IMPL, 0)
+    assert ll.shape == (2048, 8)
