@@ -140,6 +140,20 @@ int ipn_correlate(ipn_ctx* ctx, int64_t n1, const double* t1, const double* c1, 
                   int64_t i_beg_1, int64_t n_max_1, double fscale, double dt_1, double dt_2, int64_t n_sum_2,
                   double* arr_dt, double* arr_chi);
 
+/* ---- sky post-processing: credible regions on the pixel grid (next-row N4) ------------------------------
+ * replaces the KDE -> multi-order-map -> MOC route  pyipn/fit.py:193-206 (_build_moc_map) and :328-347
+ * (_contour_more_detectors: MOC.from_valued_healpix_cells(uniq, prob, cumul_to=level)) for likelihoods that are
+ * already on a pixel grid (ipn_loglik_sky_grid):
+ *   L[p] = logsumexp_s ll[p*S + s] - log S + log_weight[p]   (log_weight may be NULL: equal-area pixels, flat prior)
+ *   prob[p] = exp(L[p] - *log_norm),  *log_norm = logsumexp_p L[p]
+ *   order   = pixel indices by decreasing prob (stable: ties keep increasing pixel index)
+ *   level[p] = cumulative prob in that order up to and including p; region(c) = {p : level[p] - prob[p] < c}
+ * ll must not contain NaN or +inf and must have at least one finite entry (host entry point checks). */
+int ipn_sky_credible(ipn_ctx* ctx, int64_t P, int64_t S, const double* ll, const double* log_weight, double* prob,
+                     double* level, int64_t* order, double* log_norm);
+int ipn_sky_credible_dev(ipn_ctx* ctx, int64_t P, int64_t S, const double* d_ll, const double* d_log_weight,
+                         double* d_prob, double* d_level, int64_t* d_order, double* d_log_norm);
+
 /* ---- device micro-benchmarks used by bench.py for the roofline denominators ------------------------
  * which: 0 = FP32 FMA loop (returns TFLOP/s), 1 = MUFU.EX2 loop (returns Tops/s). */
 int ipn_microbench(ipn_ctx* ctx, int which, double* result);

@@ -433,3 +433,64 @@ def dtcc_interval(arr_dt, arr_chi, nDOF, fRijMin, nMin, nSigma):
         i += 1
         fRij = arr_chi[i]
     return arr_dt[i], dTupper, fSigma
+
+
+# ----------------------------------------------------------------------------------------------
+# sky post-processing.  Parity UNPINNED: astropy / mocpy / ligo.skymap are not
+# installed, so the reference functions cannot be run here; these restate their documented arithmetic.
+# ----------------------------------------------------------------------------------------------
+C_KM_S_ASTROPY = 299792.458  # astropy.constants.c in km/s, what utils/timing.py uses (the Stan models use 299792.46)
+
+
+def theta_from_time_delay(dt, distance):
+    """utils/timing.py:14-23.  Annulus half-opening angle: arccos(round(c dt / distance, 15)), dt in s, distance in km."""
+    return np.arccos(np.around(C_KM_S_ASTROPY * np.asarray(dt, np.float64) / np.asarray(distance, np.float64), 15))
+
+
+def calculate_distance_and_norm(p1, p2):
+    """utils/timing.py:26-59 on plain km vectors: d = p2 - p1 -> (|d|, d/|d|, ra, dec) with ra in [0, 2 pi)
+    (astropy's longitude wrap) and dec = asin(z/|d|), both in radians."""
+    d = np.asarray(p2, np.float64) - np.asarray(p1, np.float64)
+    distance = np.sqrt(np.sum(d * d))
+    n = d / distance
+    ra = np.arctan2(n[1], n[0]) % (2.0 * np.pi)
+    dec = np.arcsin(n[2])
+    return distance, n, ra, dec
+
+
+def localize_grb(sc_pos, T0):
+    """universe.py:670-697 (localize_GRB) with calculate_annulus (:364-386): for every detector pair (i < j) the row
+    M = unit vector from i to j and b = cos(theta_ij), theta from dt = T0[i] - T0[j]; least squares M g = b."""
+    from itertools import combinations
+
+    sc_pos = np.asarray(sc_pos, np.float64)
+    M, b = [], []
+    for i, j in combinations(range(sc_pos.shape[0]), 2):
+        distance, n, _, _ = calculate_distance_and_norm(sc_pos[i], sc_pos[j])
+        theta = theta_from_time_delay(T0[i] - T0[j], distance)
+        M.append(n)
+        b.append(np.cos(theta))
+    g = np.linalg.lstsq(np.array(M), np.array(b), rcond=None)[0]
+    return g
+
+
+def sky_credible(ll, log_weight=None):
+    """Greedy credible levels on a pixel grid, the grid-native replacement of fit.py:193-206 + :328-347
+    (KDE -> multi-order map -> MOC.from_valued_healpix_cells(..., cumul_to=c)).  ll (P,) or (P, S)."""
+    ll = np.asarray(ll, np.float64)
+    if ll.ndim == 1:
+        ll = ll[:, None]
+    P, S = ll.shape
+    m = ll.max(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        L = np.where(np.isfinite(m), m + np.log(np.sum(np.exp(ll - np.where(np.isfinite(m), m, 0.0)[:, None]), axis=1)) - np.log(S), m)
+    if log_weight is not None:
+        L = L + np.asarray(log_weight, np.float64)
+    mx = L.max()
+    e = np.exp(L - mx)
+    tot = e.sum()
+    prob = e / tot
+    order = np.argsort(-prob, kind="stable")
+    level = np.empty(P)
+    level[order] = np.cumsum(prob[order])
+    return prob, level, order, mx + np.log(tot)

@@ -10,6 +10,8 @@ from .lightcurve import BinnedLightCurve, LightCurve  # noqa: F401
 from .likelihood import loglik_delay_grid, loglik_sky_grid, sky_delays, time_delay  # noqa: F401
 from .params import fold_draws  # noqa: F401
 from .rff import RFF, RFF_multiscale  # noqa: F401
+from .sky import (calculate_annulus, calculate_distance_and_norm, credible_regions, grb_phi_theta, localize_GRB,  # noqa: F401
+                  theta_from_time_delay)
 from .universe import Detector, GRB, Universe  # noqa: F401
 
 __version__ = "0.1.0"

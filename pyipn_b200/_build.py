@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libipn_b200.so")
 OBJDIR = os.path.join(CSRC, "build")
 
-SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu", "correlate.cu", "binning.cu", "thinning.cu"]
+SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu", "correlate.cu", "binning.cu", "thinning.cu", "sky_post.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

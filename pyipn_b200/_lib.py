@@ -31,7 +31,7 @@ EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
     "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
-    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench",
+    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench", "ipn_sky_credible", "ipn_sky_credible_dev",
 )
 
 
@@ -93,6 +93,9 @@ def load_library():
         lib.ipn_correlate.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_double, C.c_double,
                                       C.c_double, _i64, _p, _p]
         lib.ipn_microbench.argtypes = [_p, C.c_int, C.POINTER(C.c_double)]
+        sky_args = [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]
+        lib.ipn_sky_credible.argtypes = sky_args
+        lib.ipn_sky_credible_dev.argtypes = sky_args
         _lib = lib
         return lib
 
@@ -284,6 +287,26 @@ class Context:
                                                    float(dt_1), float(dt_2), int(n_sum_2), _ptr(arr_dt), _ptr(arr_chi)))
         return arr_dt, arr_chi
 
+    def sky_credible(self, ll, log_weight=None):
+        """Credible-region products of a per-pixel log-likelihood: ``ll`` is (P,) or (P, S) (draws are marginalised).
+
+        Returns ``(prob, level, order, log_norm)``: normalised pixel probabilities, the cumulative probability at which
+        each pixel enters the greedy (highest-density-first) region, the pixels in that order, and the log normaliser."""
+        ll = _f64(ll)
+        if ll.ndim == 1:
+            ll = ll[:, None]
+        if ll.ndim != 2:
+            raise ValueError("ll must be (P,) or (P, S)")
+        ll = np.ascontiguousarray(ll)
+        P, S = ll.shape
+        lw = None if log_weight is None else _f64(log_weight, (P,), "log_weight")
+        prob, level = np.empty(P), np.empty(P)
+        order = np.empty(P, dtype=np.int64)
+        log_norm = np.empty(1)
+        _check(self._lib, self._lib.ipn_sky_credible(self._h, P, S, _ptr(ll), None if lw is None else _ptr(lw), _ptr(prob),
+                                                      _ptr(level), _ptr(order), _ptr(log_norm)))
+        return prob, level, order, float(log_norm[0])
+
     def poisson_counts(self, exposure, rates, bkg, seed):
         rates = np.atleast_2d(_f64(rates))
         S, T = rates.shape
@@ -304,6 +327,10 @@ class Context:
         _check(self._lib, self._lib.ipn_loglik_delay_grid_dev(
             self._h, T, _p(d_time), _p(d_exposure), _p(d_counts), S, J, _p(d_omega), _p(d_a), _p(d_b), _p(d_amp),
             _p(d_bkg), G, _p(d_delays), _p(d_ll)))
+
+    def sky_credible_dev(self, P, S, d_ll, d_log_weight, d_prob, d_level, d_order, d_log_norm):
+        _check(self._lib, self._lib.ipn_sky_credible_dev(self._h, P, S, _p(d_ll), _p(d_log_weight) if d_log_weight else None,
+                                                          _p(d_prob), _p(d_level), _p(d_order), _p(d_log_norm)))
 
     def poisson_counts_dev(self, T, d_exposure, S, d_rates, d_bkg, seed, d_out):
         _check(self._lib, self._lib.ipn_poisson_counts_dev(self._h, T, _p(d_exposure), S, _p(d_rates), _p(d_bkg),

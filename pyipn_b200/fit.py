@@ -169,3 +169,11 @@ class Fit(object):
         omega, a, b = self.folded()
         return loglik_sky_grid(stan_data["N_time_bins"], stan_data["time"], stan_data["exposure"], stan_data["counts"],
                                stan_data["sc_pos"], ghat, omega, a, b, amp, np.atleast_2d(self._background))
+
+    def sky_credible(self, stan_data, ghat, levels=(0.68, 0.95), pixel_area=None):
+        """Draw-marginal credible regions on the sky grid ``ghat`` (P, 3): ``sky_grid_loglik`` followed by
+        ``pyipn_b200.sky.credible_regions`` (grid-native replacement of _build_moc_map / _contour_more_detectors,
+        pyipn/fit.py:193-206, 328-347)."""
+        from .sky import credible_regions
+
+        return credible_regions(self.sky_grid_loglik(stan_data, ghat), levels=levels, pixel_area=pixel_area)
