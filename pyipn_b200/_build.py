@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("IPN_NVCC_EXTRA", "").split()  # e.g. -DIPN_TC_EPI_WARPS=16 -DIPN_TC_GCOLS=8 for kernel experiments
 
 
 def _nvcc() -> str:

@@ -36,9 +36,16 @@ constexpr int TN = 32;        // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
-constexpr int EPI_WARPS = 12;      // 3 per TMEM lane quarter (and per SM sub-partition) rotating over 8-column groups
+#ifndef IPN_TC_EPI_WARPS
+#define IPN_TC_EPI_WARPS 12
+#endif
+#ifndef IPN_TC_GCOLS
+#define IPN_TC_GCOLS 16
+#endif
+constexpr int EPI_WARPS = IPN_TC_EPI_WARPS;  // 3 per TMEM lane quarter (and per SM sub-partition) rotating over column groups
 constexpr int EPI_SLOTS = EPI_WARPS / 4;
-constexpr int GCOLS = 16;          // columns per epilogue work unit (two batches of 8)
+constexpr int GCOLS = IPN_TC_GCOLS;          // columns per epilogue work unit (batches of 8)
+constexpr int NH = GCOLS / 8;
 constexpr int GROUPS = TN / GCOLS; // work units per tile and lane quarter
 constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, group) and tile
 constexpr int NTHREADS = (3 + EPI_WARPS) * 32;
@@ -56,7 +63,9 @@ constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n 
 // tile % (a multiple of 3): all uses of one barrier then belong to the same warps, and the others never look at it.
 constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks (multiple of 3)
 constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6 (2 TMEM buffers x ownership period 3)
-static_assert(NCST % EPI_SLOTS == 0 && NTF % EPI_SLOTS == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after which the group -> slot assignment repeats
+static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
 constexpr int NBST = 4;                    // depth of the Phi digit-plane ring
 constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
 }  // namespace tc
@@ -754,15 +763,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 for (; cg < GROUPS; cg += EPI_SLOTS) {
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
-                    int s2[8], s3[8], s4[8], s5[8], r2[8], r3[8], r4[8], r5[8];
-                    tc_ld8(t0 + 0 * TN, s2);
-                    tc_ld8(t0 + 1 * TN, s3);
-                    tc_ld8(t0 + 2 * TN, s4);
-                    tc_ld8(t0 + 3 * TN, s5);
-                    tc_ld8(t0 + 0 * TN + 8, r2);
-                    tc_ld8(t0 + 1 * TN + 8, r3);
-                    tc_ld8(t0 + 2 * TN + 8, r4);
-                    tc_ld8(t0 + 3 * TN + 8, r5);
+                    int acc[NH][NLEV][8];
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+#pragma unroll
+                        for (int lev = 0; lev < NLEV; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
                     tc_wait_ld();
                     // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
                     tc_fence_before();
@@ -773,16 +778,22 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                         while (clock64() - d0 < (long long)p.epi_delay * (1 + ((warp * 7 + tile_seq) & 3))) {}
                     }
                     if (p.skip_math == 1 || (p.skip_math == 2 && quarter == (MMA_WARP & 3))) {
-                        slo += __int_as_float(s2[0] ^ s3[1] ^ s4[2] ^ s5[3] ^ r2[0] ^ r3[1] ^ r4[2] ^ r5[3]) * 0.0f;
-                    } else if (hifi) {
-                        epi_units8_hifi(s2, s3, s4, s5, cst, ksd, hacc);
-                        epi_units8_hifi(r2, r3, r4, r5, cst + 8, ksd, hacc);
-                    } else if (has_counts) {
-                        epi_units8<true>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                        epi_units8<true>(r2, r3, r4, r5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                        int x = 0;
+#pragma unroll
+                        for (int h = 0; h < NH; ++h)
+#pragma unroll
+                            for (int lev = 0; lev < NLEV; ++lev) x ^= acc[h][lev][(h + lev) & 7];
+                        slo += __int_as_float(x) * 0.0f;
                     } else {
-                        epi_units8<false>(s2, s3, s4, s5, cst, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
-                        epi_units8<false>(r2, r3, r4, r5, cst + 8, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            if (hifi)
+                                epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
+                            else if (has_counts)
+                                epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                            else
+                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(c_empty + cs);

@@ -1,36 +1,40 @@
 // Direct evaluation of the RFF intensity  amp_s * exp(sum_j a_sj cos(w_sj tau) + b_sj sin(w_sj tau)),
 // tau = time_i - shift_s.   Drop-in arithmetic for pyipn/rff.py:5-29 and the draw loop pyipn/fit.py:651-691.
 //
-// One CTA handles (draw s, a tile of RFF_TILE bins); the draw's omega/a/b vectors are staged in shared
-// memory once per CTA and broadcast to all threads.  Phases are formed in fp64 (|omega tau| reaches 1e3-1e4
-// rad for sky-scale delays, SURVEY.md section 7 hard part 3), reduced to [-pi, pi] in fp64 with a two-term
-// 2*pi, and the sine/cosine pair is then evaluated with fp32 minimax polynomials on the reduced argument
-// plus a first-order correction for the fp32 rounding of the argument.  The J-term sum is accumulated in
-// fp64 so the result meets the 1e-6 relative tolerance on lambda with a wide margin.
+// One CTA handles (draw s, a tile of RFF_TILE bins); the draw's parameters are staged in shared memory once per CTA
+// and broadcast to all threads.  |omega tau| reaches 1e4-1e5 rad for sky-scale delays (SURVEY.md section 7 hard part
+// 3), so the phase needs ~48 bits -- but not fp64 arithmetic: on B200 the fp64 conversions (F2F.F64, 16 lanes/clk/SM)
+// of a per-term fp64 reduction cost more than everything else together (first version: 82 issue cycles per term).
+// Instead the phase is formed in TURNS as an fp32 double-float product:
+//   w' = omega / 2 pi = wh + wl,  tau = th + tl  (split once per draw / once per bin, in fp64)
+//   ph = fl(wh th),  e = fma(wh, th, -ph) (exact),  cross = wh tl + wl th + e          |cross| <~ 2^-23 |ph|
+//   k = rint(ph) (magic-number add, exact),  fh = ph - k (exact),  phase mod 1 = fh + cross
+// then a quadrant fold (q = rint(4 fh), y = fh - q/4 + cross, |y| <= 1/8 + eps), y -> radians with a hi/lo 2 pi and
+// the fp32 minimax sine / cosine below.  Emulated accuracy at |phase| = 1e5 rad: max 8.5e-8, rms 1.8e-8, mean 3e-11
+// -- the same as with the fp64 reduction.  The J-term sum is a Kahan sum in fp32, folded to fp64 for the final exp.
+// Terms with |ph| >= 2^22 turns (2.6e7 rad) take an fp64 side path.
 #include "ipn_common.cuh"
 
 namespace ipn {
 
 constexpr int RFF_THREADS = 256;
-constexpr int RFF_BINS_PER_THREAD = 2;
+constexpr int RFF_BINS_PER_THREAD = 4;
 constexpr int RFF_TILE = RFF_THREADS * RFF_BINS_PER_THREAD;
 
-// sin and cos of r (|r| <= pi + eps) given as fp32 hi + lo.  Quadrant fold to |y| <= pi/4 (Cody-Waite, exact
-// because |q| <= 2), then near-minimax polynomials fitted in this repo (Chebyshev-node interpolation in
-// y^2; truncation error 1.3e-11 / 8.4e-13).  Emulated fp32 accuracy: max 8.6e-8, rms 1.9e-8, mean < 1.1e-9.
-__device__ __forceinline__ void sincos_reduced(float rh, float rl, float& s, float& c) {
-    const float qf = rintf(rh * 0.636619772367581343f);
-    const int q = (int)qf;
-    float y = fmaf(qf, -1.57079637050628662109375f, rh);
-    y = fmaf(qf, 4.37113900018624283e-8f, y);
-    y += rl;
+// Near-minimax polynomials fitted in this repo (Chebyshev-node interpolation in y^2; truncation error 1.3e-11 /
+// 8.4e-13) on |y| <= pi/4.
+// pi/2-quadrant sine / cosine of 2 pi (fh + cross) turns, |fh| <= 1/2 exact, cross a small correction
+__device__ __forceinline__ void sincos_turns(float fh, float cross, float& s, float& c) {
+    const float t4 = fmaf(fh, 4.0f, 12582912.0f);  // 1.5 * 2^23 + rint(4 fh): quadrant index in the low mantissa bits
+    const float qf = t4 - 12582912.0f;
+    const int q = __float_as_int(t4);
+    float y = fmaf(qf, -0.25f, fh) + cross;         // first part exact (Sterbenz)
+    y = fmaf(y, 6.2831854820251465f, y * -1.7484555e-07f);  // radians, 2 pi as fp32 hi + lo
     const float y2 = y * y;
-    // sin(y) = y + y^3 P(y^2)
     float ps = fmaf(y2, 2.7237618209228658e-06f, -0.00019839989971813914f);
     ps = fmaf(ps, y2, 0.008333331692152657f);
     ps = fmaf(ps, y2, -0.16666666663377125f);
     const float sy = fmaf(ps * y2, y, y);
-    // cos(y) = 1 - y^2/2 + y^4 Q(y^2)
     float pc = fmaf(y2, -2.7290681690617153e-07f, 2.4800519567960354e-05f);
     pc = fmaf(pc, y2, -0.0013888887519541376f);
     pc = fmaf(pc, y2, 0.04166666666392175f);
@@ -47,9 +51,11 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
                 const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ shift,
                 const double* __restrict__ amp, double* __restrict__ out, int64_t tiles_per_draw) {
     extern __shared__ double sm[];
-    double* s_w = sm;
+    double* s_w = sm;                                     // [J] omega (fp64: side paths)
     double* s_a = sm + J;
     double* s_b = sm + 2 * J;
+    float4* s_f = reinterpret_cast<float4*>(sm + 3 * J);  // [J] (wh, wl, a, b) with w in turns per unit time
+    __shared__ unsigned int s_wmax;                       // bits of max_j |wh|
     const int64_t n_items = S * tiles_per_draw;
     int64_t cur_s = -1;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -57,10 +63,17 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
         const int64_t tile = item - s * tiles_per_draw;
         if (s != cur_s) {
             __syncthreads();
+            if (threadIdx.x == 0) s_wmax = 0u;
+            __syncthreads();
             for (int j = threadIdx.x; j < J; j += RFF_THREADS) {
-                s_w[j] = omega[s * J + j];
-                s_a[j] = a[s * J + j];
-                s_b[j] = b[s * J + j];
+                const double w = omega[s * J + j], aj = a[s * J + j], bj = b[s * J + j];
+                s_w[j] = w;
+                s_a[j] = aj;
+                s_b[j] = bj;
+                const double wt = w * 0.15915494309189534561;  // turns
+                const float wh = (float)wt;
+                s_f[j] = make_float4(wh, (float)(wt - (double)wh), (float)aj, (float)bj);
+                atomicMax(&s_wmax, __float_as_uint(fabsf(wh)));
             }
             __syncthreads();
             cur_s = s;
@@ -68,39 +81,73 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
         const double sh = shift[s];
         const double am = amp[s];
         double tau[RFF_BINS_PER_THREAD];
-        double acc[RFF_BINS_PER_THREAD];
         int64_t idx[RFF_BINS_PER_THREAD];
 #pragma unroll
         for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
             idx[u] = tile * RFF_TILE + u * RFF_THREADS + threadIdx.x;
             tau[u] = (idx[u] < T) ? (time[idx[u]] - sh) : 0.0;
-            acc[u] = 0.0;
         }
-        for (int j = 0; j < J; ++j) {
-            const double w = s_w[j], aj = s_a[j], bj = s_b[j];
+        if (kFullFp64) {
+            double acc[RFF_BINS_PER_THREAD];
 #pragma unroll
-            for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
-                const double ph = w * tau[u];
-                if (kFullFp64) {
+            for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) acc[u] = 0.0;
+            for (int j = 0; j < J; ++j) {
+#pragma unroll
+                for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
                     double sn, cs;
-                    sincos(ph, &sn, &cs);
-                    acc[u] = fma(aj, cs, fma(bj, sn, acc[u]));
-                } else {
-                    // fp64 reduction to [-pi, pi]
-                    const double kq = rint(ph * 0.15915494309189534561);
-                    double r = fma(kq, -6.283185307179586232, ph);
-                    r = fma(kq, -2.4492935982947064e-16, r);
-                    const float rh = (float)r;
-                    const float rl = (float)(r - (double)rh);
+                    sincos(s_w[j] * tau[u], &sn, &cs);
+                    acc[u] = fma(s_a[j], cs, fma(s_b[j], sn, acc[u]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RFF_BINS_PER_THREAD; ++u)
+                if (idx[u] < T) out[s * T + idx[u]] = am * exp(acc[u]);
+            continue;
+        }
+        float th[RFF_BINS_PER_THREAD], tl[RFF_BINS_PER_THREAD], sum[RFF_BINS_PER_THREAD], comp[RFF_BINS_PER_THREAD];
+        double side[RFF_BINS_PER_THREAD];
+        const float wmax = __uint_as_float(s_wmax);
+        bool big = false;
+#pragma unroll
+        for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
+            th[u] = (float)tau[u];
+            tl[u] = (float)(tau[u] - (double)th[u]);
+            sum[u] = comp[u] = 0.0f;
+            side[u] = 0.0;
+            big = big || !(fabsf(th[u]) * wmax < 4194304.0f);
+        }
+        if (big) {
+            // the magic-number rounding below needs |ph| < 2^22 turns (2.6e7 rad): fp64 side path, never taken in practice
+            for (int j = 0; j < J; ++j) {
+#pragma unroll
+                for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
+                    double sn, cs;
+                    sincos(s_w[j] * tau[u], &sn, &cs);
+                    side[u] = fma(s_a[j], cs, fma(s_b[j], sn, side[u]));
+                }
+            }
+        } else {
+            for (int j = 0; j < J; ++j) {
+                const float4 f = s_f[j];
+#pragma unroll
+                for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
+                    const float ph = f.x * th[u];
+                    const float e = fmaf(f.x, th[u], -ph);
+                    const float cross = fmaf(f.x, tl[u], fmaf(f.y, th[u], e));
+                    const float k = (ph + 12582912.0f) - 12582912.0f;
                     float sn, cs;
-                    sincos_reduced(rh, rl, sn, cs);
-                    acc[u] = fma(aj, (double)cs, fma(bj, (double)sn, acc[u]));
+                    sincos_turns(ph - k, cross, sn, cs);
+                    const float v = fmaf(f.w, sn, f.z * cs);
+                    const float yk = v - comp[u];  // Kahan
+                    const float t = sum[u] + yk;
+                    comp[u] = (t - sum[u]) - yk;
+                    sum[u] = t;
                 }
             }
         }
 #pragma unroll
         for (int u = 0; u < RFF_BINS_PER_THREAD; ++u)
-            if (idx[u] < T) out[s * T + idx[u]] = am * exp(acc[u]);
+            if (idx[u] < T) out[s * T + idx[u]] = am * exp(((double)sum[u] - (double)comp[u]) + side[u]);
     }
 }
 
@@ -111,7 +158,7 @@ int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int6
     if (items == 0) return IPN_OK;
     const int64_t max_grid = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(items < max_grid ? items : max_grid);
-    const size_t smem = 3 * (size_t)J * sizeof(double);
+    const size_t smem = 3 * (size_t)J * sizeof(double) + (size_t)J * sizeof(float4);
     const bool full64 = getenv("IPN_RFF_FP64") != nullptr;
     if (full64)
         rff_eval_kernel<true><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S, (int)J, omega, a, b, shift, amp,

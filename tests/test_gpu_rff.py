@@ -70,6 +70,18 @@ def test_rff_eval_huge_phases(ctx):
         np.testing.assert_allclose(got[s], np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])), rtol=RTOL)
 
 
+def test_rff_eval_phases_beyond_fp32_reduction(ctx):
+    """|omega tau| / 2 pi >= 2^22 turns: the kernel must switch to its fp64 side path (per thread), not lose the phase."""
+    rng = np.random.default_rng(10)
+    time = np.concatenate([np.linspace(0.0, 10.0, 700), 6.0e4 + np.linspace(0, 1, 700)])  # small and huge phases mixed
+    omega = rng.normal(size=(1, 20)) * 800.0
+    a = rng.normal(size=(1, 20)) * 0.1
+    b = rng.normal(size=(1, 20)) * 0.1
+    got = ctx.rff_eval(time, omega, a, b, np.zeros(1), np.ones(1))
+    assert np.abs(omega).max() * 6.0e4 / (2 * np.pi) > 2**22
+    np.testing.assert_allclose(got[0], np.exp(orc.log_intensity_folded(time, omega[0], a[0], b[0])), rtol=RTOL)
+
+
 def test_argument_errors(ctx):
     from pyipn_b200 import IpnError
 
