@@ -266,7 +266,16 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
     const bool valid = pos < T;
     const int64_t i = valid ? perm[pos] : 0;
     const double t = valid ? time[i] : 0.0;
+    const float th = (float)t, tl = (float)(t - (double)(float)t);
     uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
+    // omega / 2 pi of this draw as fp32 hi + lo: the phases are formed without fp64 arithmetic (sincos_phase_df)
+    __shared__ float2 s_w[IPN_MAX_J];
+    for (int j = threadIdx.x; j < J; j += 256) {
+        const double wt = omega[s * J + j] * 0.15915494309189534561;
+        const float wh = (float)wt;
+        s_w[j] = make_float2(wh, (float)(wt - (double)wh));
+    }
+    __syncthreads();
     for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
         alignas(16) int8_t d[3][16];
 #pragma unroll
@@ -276,7 +285,8 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
             if (valid) {
                 if (k < 2 * J) {
                     float sn, cn;
-                    sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
+                    const float2 w = s_w[k >> 1];
+                    if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
                     q0 = __float2int_rn(cn * 4194304.0f);  // cos row
                     q1 = __float2int_rn(sn * 4194304.0f);  // sin row
                 } else {

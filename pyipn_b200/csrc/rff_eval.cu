@@ -13,37 +13,13 @@
 // the fp32 minimax sine / cosine below.  Emulated accuracy at |phase| = 1e5 rad: max 8.5e-8, rms 1.8e-8, mean 3e-11
 // -- the same as with the fp64 reduction.  The J-term sum is a Kahan sum in fp32, folded to fp64 for the final exp.
 // Terms with |ph| >= 2^22 turns (2.6e7 rad) take an fp64 side path.
-#include "ipn_common.cuh"
+#include "loglik_common.cuh"  // sincos_turns
 
 namespace ipn {
 
 constexpr int RFF_THREADS = 256;
 constexpr int RFF_BINS_PER_THREAD = 4;
 constexpr int RFF_TILE = RFF_THREADS * RFF_BINS_PER_THREAD;
-
-// Near-minimax polynomials fitted in this repo (Chebyshev-node interpolation in y^2; truncation error 1.3e-11 /
-// 8.4e-13) on |y| <= pi/4.
-// pi/2-quadrant sine / cosine of 2 pi (fh + cross) turns, |fh| <= 1/2 exact, cross a small correction
-__device__ __forceinline__ void sincos_turns(float fh, float cross, float& s, float& c) {
-    const float t4 = fmaf(fh, 4.0f, 12582912.0f);  // 1.5 * 2^23 + rint(4 fh): quadrant index in the low mantissa bits
-    const float qf = t4 - 12582912.0f;
-    const int q = __float_as_int(t4);
-    float y = fmaf(qf, -0.25f, fh) + cross;         // first part exact (Sterbenz)
-    y = fmaf(y, 6.2831854820251465f, y * -1.7484555e-07f);  // radians, 2 pi as fp32 hi + lo
-    const float y2 = y * y;
-    float ps = fmaf(y2, 2.7237618209228658e-06f, -0.00019839989971813914f);
-    ps = fmaf(ps, y2, 0.008333331692152657f);
-    ps = fmaf(ps, y2, -0.16666666663377125f);
-    const float sy = fmaf(ps * y2, y, y);
-    float pc = fmaf(y2, -2.7290681690617153e-07f, 2.4800519567960354e-05f);
-    pc = fmaf(pc, y2, -0.0013888887519541376f);
-    pc = fmaf(pc, y2, 0.04166666666392175f);
-    const float cy = fmaf(fmaf(pc, y2, -0.5f), y2, 1.0f);
-    const float ss = (q & 1) ? cy : sy;
-    const float cc = (q & 1) ? sy : cy;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
-}
 
 template <bool kFullFp64>
 __global__ void __launch_bounds__(RFF_THREADS)
