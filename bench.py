@@ -303,4 +303,16 @@ def main():
 
 
 if __name__ == "__main__":
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 when
+    # NCCL_DEBUG is set on the box), so everything else is sent to stderr and only json lines reach the real stdout.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 - the two json prints above go to the saved stdout
+        kw.setdefault("file", _real_stdout)
+        _print(*args, **kw)
+        _real_stdout.flush()
+
     main()
