@@ -90,7 +90,8 @@ class ClockSampler(threading.Thread):
 
 
 def run_reference(a, rank, world):
-    """The reference's CPU implementation of the path (oracle port; the reference itself is Python and cannot travel)."""
+    """The reference's CPU implementation of the path: the C restatement of its arithmetic (oracle/ipn_oracle.c) on all
+    host cores; the reference itself is Python + numba and cannot travel to the GPU box."""
     if rank != 0:
         return
     from oracle.cpu_bench import time_oracle

@@ -34,8 +34,40 @@ def _worker(args):
     return time.perf_counter() - t0, out
 
 
-def time_oracle(workload, delays_per_task=8, tasks_per_core=1, cores=None):
-    """Returns dict(value=units/s, cores, sample, seconds).  units = (delay, draw) pairs x bins."""
+def time_c_oracle(workload, pairs_per_core=32, cores=None):
+    """The plain-C restatement (oracle/ipn_oracle.c: scalar libm calls in the reference's evaluation order, which is what
+    numba makes of rff.py) on ``cores`` threads.  Returns dict(value=units/s, cores, sample, seconds)."""
+    from oracle import c_oracle as corc
+
+    cores = cores or os.cpu_count() or 1
+    corc.set_threads(cores)
+    T = len(workload["time"])
+    G = len(workload["delays"])
+    S = workload["omega"].shape[0]
+    n_delays = max(1, cores * pairs_per_core // S)
+    idx = (np.arange(n_delays) * 37) % G
+    args = (workload["counts"], workload["time"], workload["exposure"], workload["omega"], workload["a"], workload["b"],
+            workload["amp"], workload["bkg"])
+    corc.loglik_delay_grid(*args, workload["delays"][idx[: max(1, cores // S)]])  # warm-up: page-in, thread start
+    t0 = time.perf_counter()
+    corc.loglik_delay_grid(*args, workload["delays"][idx])
+    wall = time.perf_counter() - t0
+    corc.set_threads(0)
+    units = n_delays * S * T
+    return dict(value=units / wall, cores=cores, seconds=wall,
+                sample=f"{n_delays * S} (delay,draw) pairs x {T} bins on {cores} threads (C restatement of rff.py + Stan "
+                       f"poisson_lpmf, float64, scalar libm)")
+
+
+def time_oracle(workload, delays_per_task=8, tasks_per_core=1, cores=None, use_c=True):
+    """Returns dict(value=units/s, cores, sample, seconds).  units = (delay, draw) pairs x bins.  The C restatement is
+    timed when it is available (it runs at the speed of the reference's numba-compiled loops); the numpy port, one
+    process per core, is the fall-back."""
+    if use_c:
+        try:
+            return time_c_oracle(workload, cores=cores)
+        except Exception as exc:  # no compiler and no prebuilt library: say so and time the numpy port
+            print(f"[cpu_bench] C oracle unavailable ({exc}); timing the numpy port", flush=True)
     cores = cores or os.cpu_count() or 1
     T = len(workload["time"])
     G = len(workload["delays"])
