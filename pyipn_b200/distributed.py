@@ -44,28 +44,85 @@ def gather_columns(local_block, n_total: int, group=None):
     return torch.cat([recv[r, :, : sizes[r]] for r in range(world)], dim=1)
 
 
-def loglik_delay_grid_sharded(time, exposure, counts, omega, a, b, amp, bkg, delays, compute=None, device=None, group=None):
-    """Draw-sharded delay grid: every rank returns the full ``(G, S)`` float64 numpy array.
+def gather_rows(local_block, n_total: int, group=None):
+    """All-gather per-rank ``(G_local, S)`` blocks (ragged G_local allowed) into the full ``(n_total, S)``: the
+    grid-point-sharded twin of ``gather_columns`` (config 2: delays, config 4: pixels)."""
+    return gather_columns(local_block.t().contiguous(), n_total, group=group).t().contiguous()
 
-    ``compute(time, exposure, counts, omega, a, b, amp, bkg, delays) -> (G, S_local)`` defaults to the CUDA library on
-    this rank's GPU; the CPU tests inject their own callable to exercise the sharding/gather logic under gloo."""
+
+def loglik_delay_grid_sharded(time, exposure, counts, omega, a, b, amp, bkg, delays, compute=None, device=None, group=None,
+                              shard="draws"):
+    """Sharded delay grid: every rank returns the full ``(G, S)`` float64 numpy array.
+
+    ``shard="draws"`` (config 3: many posterior draws) gives each rank a slice of the draws, ``shard="delays"`` (config 2:
+    one draw, 4096 delays) a slice of the delays.  ``compute(time, exposure, counts, omega, a, b, amp, bkg, delays) ->
+    (G_local, S_local)`` defaults to the CUDA library on this rank's GPU; the CPU tests inject their own callable to
+    exercise the sharding/gather logic under gloo."""
     import torch
     import torch.distributed as dist
 
+    if shard not in ("draws", "delays"):
+        raise ValueError("shard must be 'draws' or 'delays'")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    S = np.atleast_2d(omega).shape[0]
-    lo, hi = shard_bounds(S, rank, world)
+    omega, a, b = np.atleast_2d(omega), np.atleast_2d(a), np.atleast_2d(b)
+    amp, bkg, delays = np.atleast_1d(amp), np.atleast_1d(bkg), np.atleast_1d(delays)
+    S, G = omega.shape[0], delays.shape[0]
     if compute is None:
         from ._lib import default_context
 
         compute = default_context().loglik_delay_grid
-    sl = slice(lo, hi)
-    local = compute(time, exposure, counts, np.atleast_2d(omega)[sl], np.atleast_2d(a)[sl], np.atleast_2d(b)[sl],
-                    np.atleast_1d(amp)[sl], np.atleast_1d(bkg)[sl], delays)
+    if shard == "draws":
+        sl = slice(*shard_bounds(S, rank, world))
+        local = compute(time, exposure, counts, omega[sl], a[sl], b[sl], amp[sl], bkg[sl], delays)
+    else:
+        sl = slice(*shard_bounds(G, rank, world))
+        local = compute(time, exposure, counts, omega, a, b, amp, bkg, delays[sl])
     t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     if device is not None:
         t = t.to(device)
-    return gather_columns(t, S, group=group).cpu().numpy()
+    full = gather_columns(t, S, group=group) if shard == "draws" else gather_rows(t, G, group=group)
+    return full.cpu().numpy()
+
+
+def loglik_sky_grid_sharded(nbins, time, exposure, counts, sc_pos, ghat, omega, a, b, amp, bkg, compute=None, device=None,
+                            group=None):
+    """Pixel-sharded sky grid (config 4): every rank evaluates all detectors for a contiguous slice of the directions, so
+    the detector sum stays local; one all-gather returns the full ``(P, S)`` array on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ghat = np.atleast_2d(np.asarray(ghat, dtype=np.float64))
+    P = ghat.shape[0]
+    if compute is None:
+        from ._lib import default_context
+
+        compute = default_context().loglik_sky_grid
+    lo, hi = shard_bounds(P, rank, world)
+    local = compute(nbins, time, exposure, counts, sc_pos, ghat[lo:hi], omega, a, b, amp, bkg)
+    t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    return gather_rows(t, P, group=group).cpu().numpy()
+
+
+def draw_marginal_logsumexp(ll_local, n_draws_total: int, group=None):
+    """``log (1/S) sum_s exp(ll[g, s])`` over draws that are sharded across ranks: ``ll_local`` is this rank's ``(G, S_local)``
+    torch block.  One all-reduce(MAX) and one all-reduce(SUM) of G doubles."""
+    import math
+
+    import torch
+    import torch.distributed as dist
+
+    if ll_local.shape[1] > 0:
+        m = ll_local.max(dim=1).values
+    else:
+        m = torch.full((ll_local.shape[0],), -math.inf, dtype=ll_local.dtype, device=ll_local.device)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    safe = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    acc = torch.exp(ll_local - safe[:, None]).sum(dim=1)
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return torch.where(torch.isfinite(m), safe + torch.log(acc) - math.log(n_draws_total), m)
 
 
 def global_argmax(ll_local, lo: int, group=None):
