@@ -43,7 +43,8 @@ extern "C" {
 #define IPN_OPT_LOGLIK_IMPL 1 /* 0 = auto (default), 1 = FP32-pipe contraction, 2 = tcgen05 sliced-integer contraction */
 #define IPN_OPT_PRECISE_W 2   /* FP32-pipe path only: 1 = hi/lo split delay table (default), 0 = single fp32 table */
 #define IPN_OPT_DRAW_BATCH 3  /* max draws per internal batch (bounds the delay-table scratch); 0 = auto     */
-#define IPN_OPT_HIFI 4        /* tcgen05 path epilogue: 0 = auto (fp64 when sum n_i^2 > 1e6), 1 = fp64, 2 = fp32          */
+#define IPN_OPT_HIFI 4        /* tcgen05 path epilogue: 0 = auto (per draw: fp32, compensated fp32 when sum n_i^2 > 1e6,
+                                 fp64 when > 4e7), 1 = fp64, 2 = plain fp32, 3 = compensated fp32                   */
 
 typedef struct ipn_ctx ipn_ctx;
 

@@ -73,7 +73,7 @@ constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224)
 struct TcDraw {
     float ks;     // kappa = 2^-12 / sigma
     float sigma;  // power of two
-    int hifi;     // 1: fp64 epilogue for this draw
+    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64
     int pad;
 };
 
@@ -133,10 +133,13 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     t.ks = (float)ldexp(1.0, -12 - e);
     // fp32 epilogue error model: rms |dll| ~ 3.5e-8 ln2 y sqrt(sum n_i^2) with y ~ max(1, log2(A/B)) the size of
     // log2(1+u).  Above ~2.5e-5 nats rms predicted (bright, coarsely binned data, or a source far above the background) the
-    // draw is evaluated with the fp64 epilogue.  flags[1]: 0 auto, 1 always, 2 never.
+    // draw is evaluated with the compensated fp32 epilogue, above ~2.5e-4 with the fp64 one.  flags[1] = IPN_OPT_HIFI:
+    // 0 auto, 1 always fp64, 2 always plain fp32, 3 always compensated fp32.
     const double sumsq = *reinterpret_cast<const double*>(flags + 2);
     const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
-    t.hifi = flags[1] == 1 ? 1 : (flags[1] == 2 ? 0 : (ysc * ysc * sumsq > 1.0e6 ? 1 : 0));
+    // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
+    const double crit = ysc * ysc * sumsq;
+    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0))));
     t.pad = 0;
     td[sl] = t;
 }
@@ -522,8 +525,55 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
     ssum = tt;
 }
 
+// Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
+// not the exponent or the logarithm but three roundings of O(n)-sized quantities: n*y0, kappa*u and their difference
+// (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of eight such terms.  Here the two products and the
+// difference are formed as fp32 double-floats (exact FMA error terms, TwoSum), the small parts go to the `slo` sum, and
+// every term takes its own Kahan step.  ~11 more instructions per (delay, bin); remaining error ~3.7e-8 sqrt(sum n_i^2)
+// nats rms (measured: 1e-3 max at sum n_i^2 = 1.1e8) from the 2^(-y0) refinement of the logarithm, hence the hand-over to
+// the fp64 epilogue at sum n_i^2 = 4e7.
+template <bool HC>
+__device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                                const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
+                                                float mks8, float& ssum, float& scomp, float& slo) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
+        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
+        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
+        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
+        const float u = exp2_hilo(xh, xl);
+        // kappa u = q + (eq + klo u), q = fl(khi u)
+        const float q = c.y * u;
+        float small = fmaf(c.z, u, fmaf(c.y, u, -q));
+        float d = -q;
+        if (HC) {
+            const float w = 1.0f + u;
+            const float ew = u - (w - 1.0f);
+            const float y0 = lg2_approx(w);
+            const float tm = -y0 + kMagic;
+            const float t = exp2_core(-y0 - (tm - kMagic), tm);
+            const float r = fmaf(ew, t, fmaf(w, t, -1.0f));
+            // n log2(1 + u) = pr + (epr + nl r), pr = fl(n y0)
+            const float pr = c.x * y0;
+            const float epr = fmaf(c.x, y0, -pr);
+            d = pr - q;  // TwoSum(pr, -q)
+            const float bb = d - pr;
+            const float e1 = (pr - (d - bb)) + (-q - bb);
+            small = (fmaf(c.w, r, epr) + e1) - small;
+        } else {
+            small = -small;
+        }
+        slo += small;
+        const float yk = d - scomp;  // Kahan step per term
+        const float tt = ssum + yk;
+        scomp = (tt - ssum) - yk;
+        ssum = tt;
+    }
+}
+
 // fp64 epilogue for bright / coarsely binned data (hundreds of counts per bin): the fp32 terms above carry
-// ~6e-8 n_i relative noise each, which exceeds 1e-3 nats once sum n_i^2 is large.  8x slower, selected per call.
+// ~6e-8 n_i relative noise each, which exceeds 1e-3 nats once sum n_i^2 is large.  4-5x slower, selected per draw.
 __device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8],
                                                 const int (&s5)[8], const float4* __restrict__ cst, double ksd, double& acc) {
 #pragma unroll
@@ -546,9 +596,11 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // ------------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------------
-// HIFI = true instantiation: only the draws flagged for the fp64 epilogue (every role skips the others' items), so the
-// common fp32 instantiation carries no fp64 exp2/log1p code in its instruction-cache footprint.
-template <int KSTEPS, bool HIFI>
+// One instantiation per epilogue mode (EPI_FP32 / EPI_COMP / EPI_FP64): each handles only the draws flagged for its mode
+// (every role skips the others' items), so the common fp32 instantiation carries no compensated or fp64 code in its
+// instruction-cache footprint.
+enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2 };
+template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -612,7 +664,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const bool dbg = p.dbg != nullptr;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int sl = (int)(item / items_per_draw);
-                if ((p.td[sl].hifi != 0) != HIFI) {
+                if (p.td[sl].hifi != MODE) {
                     --item_seq;  // not this instantiation's draw: the item does not exist for any role
                     continue;
                 }
@@ -658,7 +710,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = p.dbg != nullptr;
         const long long t_start = clock64();
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
-            if ((p.td[(int)(item / items_per_draw)].hifi != 0) != HIFI) {
+            if (p.td[(int)(item / items_per_draw)].hifi != MODE) {
                 --item_seq;
                 continue;
             }
@@ -746,7 +798,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = p.dbg != nullptr;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int sl = (int)(item / items_per_draw);
-            if ((p.td[sl].hifi != 0) != HIFI) continue;
+            if (p.td[sl].hifi != MODE) continue;
             const int rem = (int)(item - (int64_t)sl * items_per_draw);
             const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
             const int bt0 = chunk * p.tiles_per_chunk;
@@ -757,7 +809,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             double hacc = 0.0;
-            constexpr bool hifi = HIFI;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
@@ -797,8 +848,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     } else {
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
-                            if (hifi)
+                            if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
+                            else if (MODE == EPI_COMP && has_counts)
+                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                            else if (MODE == EPI_COMP)
+                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (has_counts)
                                 epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else
@@ -866,20 +921,27 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     double* d_R = ctx->accum.as<double>();
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
-    void (*kern)(const TcParams) = nullptr;
-    void (*kern_hifi)(const TcParams) = nullptr;
+    void (*kern[3])(const TcParams) = {nullptr, nullptr, nullptr};  // by epilogue mode
     switch (ksteps) {
-#define IPN_TC_CASE(K) case K: kern = loglik_tc_kernel<K, false>; kern_hifi = loglik_tc_kernel<K, true>; break;
+#define IPN_TC_CASE(K)                            \
+    case K:                                       \
+        kern[0] = loglik_tc_kernel<K, EPI_FP32>;  \
+        kern[1] = loglik_tc_kernel<K, EPI_COMP>;  \
+        kern[2] = loglik_tc_kernel<K, EPI_FP64>;  \
+        break;
         IPN_TC_CASE(1) IPN_TC_CASE(2) IPN_TC_CASE(3) IPN_TC_CASE(4) IPN_TC_CASE(5) IPN_TC_CASE(6)
-        default: kern = loglik_tc_kernel<7, false>; kern_hifi = loglik_tc_kernel<7, true>; break;
+        default: IPN_TC_CASE(7)
 #undef IPN_TC_CASE
     }
+    // which instantiations can have work: auto -> fp32, compensated and (rarely) fp64; forced modes -> one
+    const bool run_mode[3] = {ctx->hifi_mode == 0 || ctx->hifi_mode == 2, ctx->hifi_mode == 0 || ctx->hifi_mode == 3,
+                              ctx->hifi_mode == 0 || ctx->hifi_mode == 1};
     {
         int* trap = trap_record_device_ptr();
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    IPN_CUDA_CHECK(cudaFuncSetAttribute(kern_hifi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IPN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int m = 0; m < 3; ++m)
+        IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
@@ -930,10 +992,14 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                 p.dbg = ctx->dbg.as<unsigned long long>();
             }
             main_kernel_begin(ctx);
-            kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
-            if (ctx->hifi_mode != 2) kern_hifi<<<grid, NTHREADS, smem, ctx->stream>>>(p);  // draws flagged for the fp64 epilogue
+            for (int m = 0; m < 3; ++m) {
+                if (!run_mode[m]) continue;
+                // the per-draw modes are decided on the device, so in auto mode all three are launched; an instantiation
+                // without draws of its mode exits at once (~15 us)
+                kern[m]<<<grid, NTHREADS, smem, ctx->stream>>>(p);
+                ctx->launches += 1;
+            }
             main_kernel_end(ctx);
-            ctx->launches += ctx->hifi_mode != 2 ? 2 : 1;
             IPN_CUDA_CHECK(cudaGetLastError());
             if (want_dbg) {
                 std::vector<unsigned long long> h((size_t)grid * 8);

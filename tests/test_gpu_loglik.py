@@ -26,9 +26,10 @@ def test_delay_grid_reference_golden(ctx, loglik_golden):
     np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(g["ll"], axis=0))
 
 
-@pytest.mark.parametrize("hifi", [1, 2])
+@pytest.mark.parametrize("hifi", [1, 2, 3])
 def test_delay_grid_epilogue_modes(ctx, loglik_golden, hifi):
-    """Both epilogues of the tcgen05 path (fp64 = 1, fp32 = 2) meet the tolerance on the fixture (~27 counts/bin)."""
+    """All epilogues of the tcgen05 path (fp64 = 1, fp32 = 2, compensated fp32 = 3) meet the tolerance on the fixture
+    (~27 counts/bin, 600 bins)."""
     from pyipn_b200._lib import OPT_HIFI
 
     g = loglik_golden
@@ -256,3 +257,40 @@ def test_tc_pipeline_survives_unbalanced_roles(ctx, monkeypatch, hook):
     finally:
         ctx.set_option(OPT_LOGLIK_IMPL, 0)
     assert ll.shape == (2048, 8)
+
+
+@pytest.mark.parametrize("boost,comp_guaranteed", [(3_000.0, True), (20_000.0, False)])
+def test_compensated_epilogue_on_bright_data(ctx, boost, comp_guaranteed):
+    """1e5 bins with ~10 (sum n^2 = 2.3e7: auto picks the compensated fp32 epilogue) or ~40 counts each (sum n^2 = 6e8: auto
+    picks fp64).  The plain fp32 epilogue rounds its per-bin terms at 6e-8 n and is not guaranteed here; the compensated
+    one is up to sum n^2 = 4e7; auto mode must meet the tolerance in both."""
+    from oracle import c_oracle as corc
+    from pyipn_b200._lib import OPT_HIFI, OPT_LOGLIK_IMPL
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=100_000, G=512, S=2, boost=boost, bkg=5_000.0)
+    sumsq = float((w["counts"].astype(np.float64) ** 2).sum())
+    assert (1e7 < sumsq < 4e7) if comp_guaranteed else (2e8 < sumsq < 2e9)
+    args = (w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    idx = np.arange(0, 512, 8)
+    exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"],
+                                 w["delays"][idx])
+    # keep to the (delay, draw) pairs where the model is not grossly wrong (DESIGN.md error model: the digit-plane term scales
+    # with the residuals; with data this bright even the jittered second draw is thousands of nats off everywhere)
+    near = (exp.max() - exp) < 1.0e3
+    assert near.sum() >= 2
+    errs = {}
+    ctx.set_option(OPT_LOGLIK_IMPL, 2)
+    try:
+        for mode in (0, 3, 1, 2):
+            ctx.set_option(OPT_HIFI, mode)
+            ll = ctx.loglik_delay_grid(*args)
+            errs[mode] = float(np.abs(ll[idx] - exp)[near].max())
+            np.testing.assert_array_equal(np.argmax(ll[idx], axis=0), np.argmax(exp, axis=0))
+    finally:
+        ctx.set_option(OPT_HIFI, 0)
+        ctx.set_option(OPT_LOGLIK_IMPL, 0)
+    print(f"sum n^2 = {sumsq:.3g}: max |dll| near the maximum by epilogue mode (0 auto, 3 compensated, 1 fp64, 2 plain fp32):", errs)
+    assert errs[0] < ATOL and errs[1] < ATOL
+    if comp_guaranteed:
+        assert errs[3] < ATOL

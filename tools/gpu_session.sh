@@ -12,5 +12,5 @@ $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:loglik_tc_kernelILi7ELb0 -s 2 -c 1 -o gpurun_out/prof_bench $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:loglik_tc_kernelILi7ELi0 -s 2 -c 1 -o gpurun_out/prof_bench $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
