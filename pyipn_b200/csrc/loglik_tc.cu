@@ -20,12 +20,16 @@
 // used as the A operand from there: with both operands in shared memory the 63 MMAs of a tile would re-read
 // the 128-row A operand every time (6 KB per 32-cycle MMA = 192 B/clk, more than shared memory delivers; measured
 // ~75 cycles per MMA).  The Phi digits (B operand, 21 KB per tile) stream through a 4-stage bulk-copy ring, the
-// tiles' Poisson constants through a separate 8-deep ring.  4 level accumulators x 32 columns x 2 buffers sit in
+// tiles' Poisson constants through a separate 6-deep ring.  4 level accumulators x 32 columns x 2 buffers sit in
 // TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
 // Warp roles: 0..11 = epilogue, 12 = bulk-copy producer, 13 / 14 = MMA issuers of the even / odd tiles (13 also does the
-// tcgen05.cp of the W digits).
+// tcgen05.cp of the W digits).  Three instantiations by epilogue arithmetic (plain fp32 / compensated fp32 / fp64), each
+// working on the draws whose brightness asks for it (tc_draw_kernel decides per draw).
+// Experiment / test hooks read from the environment at every launch: IPN_TC_DEBUG (wait-cycle counters), IPN_TC_SKIP_MATH,
+// IPN_TC_SKIP_MMA, IPN_TC_ONE_ISSUER, IPN_TC_EPI_DELAY, IPN_TC_GRID, IPN_TC_CHUNK_TILES (tests/test_gpu_loglik.py uses them
+// to check that results do not depend on pacing).
 #include "loglik_common.cuh"
 
 namespace ipn {
