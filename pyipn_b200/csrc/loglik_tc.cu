@@ -36,7 +36,10 @@ namespace ipn {
 
 namespace tc {
 constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
-constexpr int TN = 32;        // bins per tile (MMA N, TMEM columns per level)
+#ifndef IPN_TC_TN
+#define IPN_TC_TN 32
+#endif
+constexpr int TN = IPN_TC_TN; // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
@@ -70,7 +73,9 @@ constexpr int NTF = 6;                     // "accumulators complete" barriers: 
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after which the group -> slot assignment repeats
 static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
-constexpr int NBST = 4;                    // depth of the Phi digit-plane ring
+constexpr int NBST = 128 / TN;             // depth of the Phi digit-plane ring (4 tiles of 32 bins: 86 KB)
+constexpr int NBUF = 256 / (NLEV * TN);    // accumulator buffers in TMEM columns [256, 512)
+static_assert(NBUF >= 2 && NBUF % 2 == 0 && NTF >= NBUF, "each accumulator buffer belongs to one issuer");
 constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
 }  // namespace tc
 
@@ -650,8 +655,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* bars = reinterpret_cast<uint64_t*>(sC0 + NCST * CONST_BYTES);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* t_empty = bars + 2;            // [2]
-    uint64_t* t_full = bars + 4;             // [NTF]
+    uint64_t* t_empty = bars + 2;            // [NBUF]
+    uint64_t* t_full = t_empty + NBUF;       // [NTF]
     uint64_t* b_full = t_full + NTF;         // [NBST]
     uint64_t* b_empty = b_full + NBST;       // [NBST]
     uint64_t* c_full = b_empty + NBST;       // [NCST]
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_empty, 1);
         mbar_init(a_tmem_full, 1);
         mbar_init(a_tmem_free, 2);
-        for (int i = 0; i < 2; ++i) mbar_init(t_empty + i, EPI_ARRIVALS);
+        for (int i = 0; i < NBUF; ++i) mbar_init(t_empty + i, EPI_ARRIVALS);
         for (int i = 0; i < NTF; ++i) mbar_init(t_full + i, 1);
         for (int i = 0; i < NBST; ++i) {
             mbar_init(b_full + i, 1);
@@ -783,7 +788,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 if ((p.one_issuer ? 0u : (tile_seq & 1)) != which) continue;
                 const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
-                const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
+                const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
                 mbar_wait_timed(b_full + st, ph, w_bf, dbg, W_B_FULL, tile_seq, prog);
                 mbar_wait_timed(t_empty + tb, tph ^ 1, w_te, dbg, W_T_EMPTY, tile_seq, prog);
                 tc_fence_after();
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             double hacc = 0.0;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const uint32_t tb = tile_seq & 1, tph = (tile_seq >> 1) & 1;
+                const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
                 // groups of this tile that belong to this warp: (tile_seq * GROUPS + cg) % EPI_SLOTS == slot
                 int cg = (int)((slot + EPI_SLOTS - (tile_seq * GROUPS) % EPI_SLOTS) % EPI_SLOTS);
@@ -937,7 +942,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
-    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (6 + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 64;
+    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 64;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -1007,14 +1012,15 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             const int64_t base_items = (int64_t)Sb * n_dt;
             if (base_items < 32 * (int64_t)ctx->sm_count) {
                 nchunk = (int)((32 * (int64_t)ctx->sm_count + base_items - 1) / base_items);
-                const int max_chunks = (n_bt + 15) / 16;  // keep >= 16 tiles per item
+                const int min_tiles = 512 / TN;  // keep >= 512 bins per item
+                const int max_chunks = (n_bt + min_tiles - 1) / min_tiles;
                 if (nchunk > max_chunks) nchunk = max_chunks;
                 if (nchunk < 1) nchunk = 1;
             }
             // ... and when there are many tiles, so that an item lasts ~0.1 ms: the 32 delay tiles that share a chunk of Phi
             // start up to one item apart (148 CTAs is not a multiple of 32), and the chunk must still be in L2 for the late
             // ones (ncu: 600-tile items re-read half of Phi from HBM, 2.2x the minimum traffic)
-            const int max_tiles = getenv("IPN_TC_CHUNK_TILES") ? atoi(getenv("IPN_TC_CHUNK_TILES")) : 128;
+            const int max_tiles = getenv("IPN_TC_CHUNK_TILES") ? atoi(getenv("IPN_TC_CHUNK_TILES")) : 4096 / TN;
             if ((n_bt + nchunk - 1) / nchunk > max_tiles) nchunk = (n_bt + max_tiles - 1) / max_tiles;
             const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
             nchunk = (n_bt + tiles_per_chunk - 1) / tiles_per_chunk;
