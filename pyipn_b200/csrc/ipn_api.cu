@@ -42,7 +42,7 @@ void set_error(const char* fmt, ...) {
     {
         n += snprintf(g_err + n, sizeof(g_err) - n, " [kernel barrier time-out: wait id %d, block %d, warp %d, parity %d, sequence %d; last wait (id:sequence) per warp:",
                       g_trap_host[0], g_trap_host[1], g_trap_host[2], g_trap_host[3], g_trap_host[4]);
-        for (int w = 0; w < 16 && n < (int)sizeof(g_err) - 24; ++w)
+        for (int w = 0; w < 24 && n < (int)sizeof(g_err) - 24; ++w)
             n += snprintf(g_err + n, sizeof(g_err) - n, " %d:%d", (int)((unsigned)g_trap_host[8 + w] >> 24), g_trap_host[8 + w] & 0xFFFFFF);
         if (n < (int)sizeof(g_err) - 2) snprintf(g_err + n, sizeof(g_err) - n, "]");
     }

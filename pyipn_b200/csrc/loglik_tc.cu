@@ -24,7 +24,7 @@
 // TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
-// Warp roles: 0..11 = epilogue, 12 = bulk-copy producer, 13 / 14 = MMA issuers of the even / odd tiles (13 also does the
+// Warp roles: 0..15 = epilogue, 16 = bulk-copy producer, 17 / 18 = MMA issuers of the even / odd tiles (17 also does the
 // tcgen05.cp of the W digits).  Three instantiations by epilogue arithmetic (plain fp32 / compensated fp32 / fp64), each
 // working on the draws whose brightness asks for it (tc_draw_kernel decides per draw).
 // Experiment / test hooks read from the environment at every launch: IPN_TC_DEBUG (wait-cycle counters), IPN_TC_SKIP_MATH,
@@ -44,12 +44,13 @@ constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
 constexpr int PP = 3;         // Phi digit planes
 #ifndef IPN_TC_EPI_WARPS
-#define IPN_TC_EPI_WARPS 12
+#define IPN_TC_EPI_WARPS 16
 #endif
 #ifndef IPN_TC_GCOLS
 #define IPN_TC_GCOLS 16
 #endif
-constexpr int EPI_WARPS = IPN_TC_EPI_WARPS;  // 3 per TMEM lane quarter (and per SM sub-partition) rotating over column groups
+constexpr int EPI_WARPS = IPN_TC_EPI_WARPS;  // 4 per TMEM lane quarter (and per SM sub-partition) rotating over column groups:
+                                             // 96 registers per thread, measured 3 % faster than 12 warps at 126
 constexpr int EPI_SLOTS = EPI_WARPS / 4;
 constexpr int GCOLS = IPN_TC_GCOLS;          // columns per epilogue work unit (batches of 8)
 constexpr int NH = GCOLS / 8;
@@ -58,18 +59,19 @@ constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, grou
 constexpr int NTHREADS = (3 + EPI_WARPS) * 32;
 // The warp scheduler favours the highest warp id among eligible warps: the two light but latency-critical roles
 // get the top ids so the epilogue warps sharing their sub-partitions cannot starve them.
-constexpr int PRODUCER_WARP = EPI_WARPS;      // 12
-constexpr int MMA_WARP = EPI_WARPS + 1;       // 13: issues the even tiles (accumulator buffer 0) and the TMEM copies of W
-constexpr int MMA_WARP2 = EPI_WARPS + 2;      // 14: issues the odd tiles (accumulator buffer 1) from another sub-partition
+constexpr int PRODUCER_WARP = EPI_WARPS;      // 16
+constexpr int MMA_WARP = EPI_WARPS + 1;       // 17: issues the even tiles (accumulator buffer 0) and the TMEM copies of W
+constexpr int MMA_WARP2 = EPI_WARPS + 2;      // 18: issues the odd tiles (accumulator buffer 1) from another sub-partition
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
 constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
 // A parity wait on an mbarrier is only sound if the waiter sees EVERY phase of that barrier (it cannot tell "two phases
-// away" from "done").  A warp of epilogue slot s owns groups with (2 tile + g) % 3 == s, so it skips every third tile; with
-// two MMA issuers tiles may also complete out of order.  Hence every barrier an epilogue warp waits on is indexed by
-// tile % (a multiple of 3): all uses of one barrier then belong to the same warps, and the others never look at it.
-constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks (multiple of 3)
-constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6 (2 TMEM buffers x ownership period 3)
+// away" from "done").  A warp of epilogue slot s owns the groups with (GROUPS tile + g) % EPI_SLOTS == s, so it skips tiles
+// (every other one with 4 slots and 2 groups, every third with 3 slots); with two MMA issuers tiles may also complete out
+// of order.  Hence every barrier an epilogue warp waits on is indexed by tile % (a multiple of the ownership period): all
+// uses of one barrier then belong to the same warps, and the others never look at it.  6 serves both 3 and 4 slots.
+constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks
+constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after which the group -> slot assignment repeats
 static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
@@ -395,7 +397,7 @@ __device__ __noinline__ void mbar_timeout(int id, uint32_t parity, uint32_t seq,
         r[2] = (int)(threadIdx.x >> 5);
         r[3] = (int)parity;
         r[4] = (int)seq;
-        for (int w = 0; w < 16; ++w) r[8 + w] = (int)prog[w];  // what every warp of the CTA was last waiting for
+        for (int w = 0; w < 24; ++w) r[8 + w] = (int)prog[w];  // what every warp of the CTA was last waiting for
         __threadfence_system();
     }
     __trap();
@@ -664,7 +666,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* a_tmem_full = c_empty + NCST;  // W digits of the current item are in tensor memory (issuer 0 -> issuer 1)
     uint64_t* a_tmem_free = a_tmem_full + 1; // both issuers' MMAs of the item have finished reading them (-> issuer 0)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_tmem_free + 1);
-    volatile uint32_t* prog = tmem_slot + 4;  // [16] last wait of every warp (time-out diagnostics)
+    volatile uint32_t* prog = tmem_slot + 4;  // [24] last wait of every warp (time-out diagnostics)
+    static_assert(NTHREADS / 32 <= 24, "prog[] holds one word per warp");
 
     // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
@@ -942,7 +945,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
-    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 64;
+    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 24 * 4;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
