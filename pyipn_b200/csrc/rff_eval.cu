@@ -32,6 +32,7 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
     double* s_b = sm + 2 * J;
     float4* s_f = reinterpret_cast<float4*>(sm + 3 * J);  // [J] (wh, wl, a, b) with w in turns per unit time
     __shared__ unsigned int s_wmax;                       // bits of max_j |wh|
+    __shared__ float s_amp2;                              // sum_j a_j^2 + b_j^2 of the draw
     const int64_t n_items = S * tiles_per_draw;
     int64_t cur_s = -1;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -50,6 +51,14 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
                 const float wh = (float)wt;
                 s_f[j] = make_float4(wh, (float)(wt - (double)wh), (float)aj, (float)bj);
                 atomicMax(&s_wmax, __float_as_uint(fabsf(wh)));
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {  // deterministic: lane-strided partial sums, butterfly reduction
+                double q = 0.0;
+                for (int j = threadIdx.x; j < J; j += 32) q += s_a[j] * s_a[j] + s_b[j] * s_b[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if (threadIdx.x == 0) s_amp2 = (float)q;
             }
             __syncthreads();
             cur_s = s;
@@ -92,8 +101,14 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
             side[u] = 0.0;
             big = big || !(fabsf(th[u]) * wmax < 4194304.0f);
         }
-        if (big) {
-            // the magic-number rounding below needs |ph| < 2^22 turns (2.6e7 rad): fp64 side path, never taken in practice
+        // Accuracy tiers by the draw's amplitude A2 = sum a^2 + b^2 (the error is absolute in log lambda and scales with it):
+        //   A2 <= 12   plain fp32 terms + Kahan sum: measured max 4.7e-7 at A2 = 4.5, i.e. 7.6e-7 at 12 (prior: median 6.7)
+        //   A2 <= 100  products and their sum as fp32 double-floats (exact FMA / TwoSum error terms): what remains is the
+        //              sin/cos error, 1.8e-8 rms per term
+        //   beyond     fp64 sincos and accumulation (also taken when the fp32 phase reduction does not apply)
+        const float amp2 = s_amp2;
+        if (big || !(amp2 <= 100.0f)) {
+            // (the magic-number rounding below needs |ph| < 2^22 turns = 2.6e7 rad)
             for (int j = 0; j < J; ++j) {
 #pragma unroll
                 for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
@@ -102,6 +117,34 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
                     side[u] = fma(s_a[j], cs, fma(s_b[j], sn, side[u]));
                 }
             }
+        } else if (amp2 > 12.0f) {
+            float lo[RFF_BINS_PER_THREAD];
+#pragma unroll
+            for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) lo[u] = 0.0f;
+            for (int j = 0; j < J; ++j) {
+                const float4 f = s_f[j];
+#pragma unroll
+                for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
+                    const float ph = f.x * th[u];
+                    const float e = fmaf(f.x, th[u], -ph);
+                    const float cross = fmaf(f.x, tl[u], fmaf(f.y, th[u], e));
+                    const float k = (ph + 12582912.0f) - 12582912.0f;
+                    float sn, cs;
+                    sincos_turns(ph - k, cross, sn, cs);
+                    const float pc = f.z * cs, epc = fmaf(f.z, cs, -pc);  // a cos, exact error
+                    const float ps = f.w * sn, eps = fmaf(f.w, sn, -ps);  // b sin, exact error
+                    const float v = pc + ps;                              // TwoSum
+                    const float bb = v - pc;
+                    const float ev = (pc - (v - bb)) + (ps - bb);
+                    lo[u] += (epc + eps) + ev;
+                    const float yk = v - comp[u];  // Kahan
+                    const float t = sum[u] + yk;
+                    comp[u] = (t - sum[u]) - yk;
+                    sum[u] = t;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) side[u] = (double)lo[u];
         } else {
             for (int j = 0; j < J; ++j) {
                 const float4 f = s_f[j];

@@ -82,6 +82,26 @@ def test_rff_eval_phases_beyond_fp32_reduction(ctx):
     np.testing.assert_allclose(got[0], np.exp(orc.log_intensity_folded(time, omega[0], a[0], b[0])), rtol=RTOL)
 
 
+@pytest.mark.parametrize("scale", [0.15, 0.45, 1.5])
+def test_rff_eval_accuracy_tiers_by_amplitude(ctx, scale):
+    """The error of the intensity is absolute in log(lambda) and scales with the draw's amplitudes; the kernel switches to
+    compensated fp32 terms (sum a^2 + b^2 > 12) and to fp64 (> 100) so that 1e-6 relative holds for all of them."""
+    rng = np.random.default_rng(int(scale * 100))
+    T, S, J = 20_000, 3, 100
+    time = np.sort(rng.uniform(0.0, 100.0, T))
+    omega = rng.normal(size=(S, J)) * np.where(np.arange(J) < J // 2, 0.05, 2.0)
+    a = rng.normal(size=(S, J)) * scale
+    b = rng.normal(size=(S, J)) * scale
+    a2 = (a * a + b * b).sum(axis=1)
+    assert (a2.max() <= 12) if scale == 0.15 else ((12 < a2.min() and a2.max() <= 100) if scale == 0.45 else a2.min() > 100)
+    shift = rng.normal(0, 0.5, S)
+    got = ctx.rff_eval(time, omega, a, b, shift, np.ones(S))
+    for s in range(S):
+        logf = orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])
+        keep = np.abs(logf) < 600.0  # exp overflows float64 beyond (both sides give inf there)
+        np.testing.assert_allclose(got[s][keep], np.exp(logf[keep]), rtol=RTOL)
+
+
 def test_argument_errors(ctx):
     from pyipn_b200 import IpnError
 
