@@ -136,8 +136,9 @@ __device__ __forceinline__ void sincos_turns(float fh, float cross, float& s, fl
     const float cy = fmaf(fmaf(pc, y2, -0.5f), y2, 1.0f);
     const float ss = (q & 1) ? cy : sy;
     const float cc = (q & 1) ? sy : cy;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
+    // signs by XOR into the sign bit: bit 1 of q for the sine, bit 1 of q + 1 for the cosine
+    s = __int_as_float(__float_as_int(ss) ^ ((q << 30) & 0x80000000));
+    c = __int_as_float(__float_as_int(cc) ^ (((q + 1) << 30) & 0x80000000));
 }
 
 // (sin, cos) of 2 pi w t for w = wh + wl (turns per unit time) and t = th + tl, all fp32 double-float splits of fp64 values:
