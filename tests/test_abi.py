@@ -65,3 +65,44 @@ def test_no_cpu_fallback_without_gpu(lib):
 
     with pytest.raises(IpnError):
         RFF(np.arange(4.0), np.ones(2), np.ones(2), np.ones(2), np.ones(2), 1.0, 1.0)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/ipn.h must be usable from C (the boundary is a C ABI, not C++): compile a C99 program against it, link it
+    with the library and call the entry points that need no GPU."""
+    import shutil
+    import subprocess
+
+    from pyipn_b200._build import build_library
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    LIB_PATH = build_library()
+    root = ROOT
+    src = tmp_path / "abi_c.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ipn.h"
+int main(void) {
+    const char* v = ipn_version();
+    if (!v || !*v) return 2;
+    /* argument errors are reported before any CUDA call */
+    int rc = ipn_rff_eval(NULL, 4, NULL, 1, 2, NULL, NULL, NULL, NULL, NULL, NULL);
+    if (rc != IPN_ERR_INVALID_ARGUMENT) return 3;
+    if (strlen(ipn_last_error()) == 0) return 4;
+    ipn_ctx* ctx = NULL;
+    rc = ipn_ctx_create(0, &ctx);
+    if (rc == IPN_OK) { ipn_ctx_destroy(ctx); printf("gpu "); }
+    else if (rc != IPN_ERR_NO_DEVICE && rc != IPN_ERR_CUDA) return 5;
+    printf("ok %s\n", v);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_c"
+    libdir = os.path.dirname(LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lipn_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
