@@ -125,6 +125,19 @@ def main():
     if a.impl == "reference":
         run_reference(a, rank, world)
         return
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: start one rank per GPU ourselves (the driver uses torchrun directly)
+        import socket
+
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        sys.stdout.flush()
+        os.dup2(_real_stdout.fileno(), 1)  # the ranks inherit the real stdout; rank 0 prints the json line there
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), *sys.argv[1:]])
+    if a.gpus != world:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE is {world}: launch one rank per GPU (torchrun --nproc-per-node {a.gpus})")
 
     import torch
     import torch.distributed as dist
