@@ -63,3 +63,30 @@ def test_c_oracle_equals_numpy_oracle(threads):
         np.testing.assert_allclose(corc.loglik_sky_grid(*sargs), orc.loglik_sky_grid(*sargs), rtol=1e-13, atol=1e-9)
     finally:
         corc.set_threads(0)
+
+
+def test_c_oracle_random_shapes_property():
+    """Hypothesis: for random small shapes (including empty axes and zero exposure) the C and numpy restatements agree."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(T=st.integers(0, 40), G=st.integers(1, 5), S=st.integers(1, 3), J=st.integers(1, 9), seed=st.integers(0, 2**31 - 1))
+    def check(T, G, S, J, seed):
+        rng = np.random.default_rng(seed)
+        time = np.sort(rng.uniform(-5, 5, T))
+        expo = rng.uniform(0.0, 0.3, T)
+        if T > 2:
+            expo[1] = 0.0  # mu = 0 with n = 0 must contribute nothing
+        omega = rng.normal(size=(S, J)) * 3.0
+        a = rng.normal(size=(S, J)) * 0.3
+        b = rng.normal(size=(S, J)) * 0.3
+        amp = np.exp(rng.normal(2.0, 1.0, S))
+        bkg = np.exp(rng.normal(1.0, 1.0, S))
+        counts = rng.poisson(expo * 20.0).astype(np.int64)
+        delays = rng.uniform(-1, 1, G)
+        got = corc.loglik_delay_grid(counts, time, expo, omega, a, b, amp, bkg, delays)
+        exp = orc.loglik_delay_grid(counts, time, expo, omega, a, b, amp, bkg, delays)
+        np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-10)
+
+    check()
