@@ -294,3 +294,42 @@ def test_compensated_epilogue_on_bright_data(ctx, boost, comp_guaranteed):
     assert errs[0] < ATOL and errs[1] < ATOL
     if comp_guaranteed:
         assert errs[3] < ATOL
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_delay_grid_random_small_shapes_property(ctx, impl):
+    """Hypothesis over small ragged shapes (bins not a multiple of 32, delays not a multiple of 128, J from 1 to 120, zero
+    exposure, zero amplitude, empty light curves): both implementations against the C oracle."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle import c_oracle as corc
+    from pyipn_b200._lib import OPT_LOGLIK_IMPL
+
+    @settings(max_examples=25, deadline=None)
+    @given(T=st.integers(0, 200), G=st.integers(1, 300), S=st.integers(1, 4), J=st.integers(1, 120), seed=st.integers(0, 2**31 - 1))
+    def check(T, G, S, J, seed):
+        rng = np.random.default_rng(seed)
+        time = np.sort(rng.uniform(0, 20, T))
+        expo = rng.uniform(0.001, 0.05, T)
+        if T > 3:
+            expo[2] = 0.0
+        omega = rng.normal(size=(S, J)) * np.where(np.arange(J) % 2 == 0, 0.1, 3.0)
+        a = rng.normal(size=(S, J)) * 0.1
+        b = rng.normal(size=(S, J)) * 0.1
+        amp = np.exp(rng.normal(5.0, 0.5, S))
+        if S > 1:
+            amp[1] = 0.0
+        bkg = np.exp(rng.normal(np.log(300.0), 0.3, S))
+        counts = rng.poisson(expo * 600.0).astype(np.int64)
+        delays = np.sort(rng.uniform(-1, 1, G))
+        got = ctx.loglik_delay_grid(time, expo, counts, omega, a, b, amp, bkg, delays)
+        exp = corc.loglik_delay_grid(counts, time, expo, omega, a, b, amp, bkg, delays)
+        assert got.shape == (G, S)
+        assert np.abs(got - exp).max() < ATOL
+
+    ctx.set_option(OPT_LOGLIK_IMPL, impl)
+    try:
+        check()
+    finally:
+        ctx.set_option(OPT_LOGLIK_IMPL, 0)
