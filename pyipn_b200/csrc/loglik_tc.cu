@@ -873,10 +873,24 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
                     int acc[NH][NLEV][8];
+                    if (NH == 2) {
+                        // one 16-column load per level instead of two 8-column ones
 #pragma unroll
-                    for (int h = 0; h < NH; ++h)
+                        for (int lev = 0; lev < NLEV; ++lev) {
+                            int v[16];
+                            tc_ld16(t0 + lev * TN, v);
 #pragma unroll
-                        for (int lev = 0; lev < NLEV; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
+                            for (int j = 0; j < 8; ++j) {
+                                acc[0][lev][j] = v[j];
+                                acc[NH - 1][lev][j] = v[8 + j];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < NH; ++h)
+#pragma unroll
+                            for (int lev = 0; lev < NLEV; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
+                    }
                     tc_wait_ld();
                     // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
                     tc_fence_before();
