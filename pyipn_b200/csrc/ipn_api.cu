@@ -318,6 +318,11 @@ static int check_grid_shapes(int64_t T, int64_t S, int64_t J, int64_t G) {
         set_error("J = %lld exceeds IPN_MAX_J = %d", (long long)J, IPN_MAX_J);
         return IPN_ERR_UNSUPPORTED;
     }
+    // kernel index types and launch geometry: bins are permuted through 32-bit indices, delay tiles (128 delays) ride in gridDim.y
+    if (T > 0x7fffffffLL || G > 65535LL * 128) {
+        set_error("grid too large for one call: T = %lld (max 2^31 - 1), G = %lld (max 8388480); split it", (long long)T, (long long)G);
+        return IPN_ERR_UNSUPPORTED;
+    }
     return IPN_OK;
 }
 
