@@ -306,7 +306,7 @@ def test_delay_grid_random_small_shapes_property(ctx, impl):
     from oracle import c_oracle as corc
     from pyipn_b200._lib import OPT_LOGLIK_IMPL
 
-    @settings(max_examples=25, deadline=None)
+    @settings(max_examples=25, deadline=None, derandomize=True, database=None)
     # the tcgen05 path holds 2 J + 8 rows in its K = 224 digit planes: J <= 108 (auto mode takes the FP32-pipe kernel beyond)
     @given(T=st.integers(0, 200), G=st.integers(1, 300), S=st.integers(1, 4), J=st.integers(1, 108 if impl == 2 else 120),
            seed=st.integers(0, 2**31 - 1))
