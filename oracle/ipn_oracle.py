@@ -23,6 +23,10 @@ Parity pinning (see DESIGN.md "Oracle"):
 * The intensity functions are pinned against the *reference's own* ``pyipn/rff.py`` (imported by file
   path in the build container) through the committed fixtures in ``tests/golden/`` (generator:
   ``tests/golden/make_golden.py``).
+* The draw loops, ``ppc_counts`` (MT19937 stream), ``bin_events`` and ``to_stan_data`` are pinned against the
+  reference's own ``_expeced_rate*`` / ``ppc_generator`` / ``get_binned_light_curve`` / ``to_stan_data``, lifted out of
+  ``fit.py`` / ``lightcurve.py`` / ``universe.py`` and run in the build container (``tests/golden/make_golden_path.py``
+  -> ``path_golden.npz``, ``tests/test_path_golden.py``).
 * The Poisson likelihood arithmetic lives in Stan math, which is not vendored by the reference and has
   no golden vector in the reference's tests  ->  **parity unpinned** at that boundary; the restatement
   follows Stan's documented ``poisson_lpmf`` (n log(mu) - mu - lgamma(n+1); mu=0,n=0 -> 0;
