@@ -110,6 +110,58 @@ def test_universe_from_dict_and_stan_data_contract():
     np.testing.assert_array_equal(u2.to_stan_data(-5.0, 20.0)["counts"], sd["counts"])
 
 
+def test_universe_from_yaml_template(tmp_path):
+    """The schema of the reference's examples/template_3.yaml (BASELINE config 1): no seed key -> 12345 (universe.py:272-277),
+    detectors registered in file order and re-ordered by arrival time when the GRB goes off."""
+    from pyipn_b200 import Universe
+
+    text = """
+grb:
+  ra: 180.
+  dec: 30.
+  distance: 500.
+  K: 500. # intensity
+  t_rise: .5
+  t_decay: 4.1
+detectors:
+  det3:
+     ra: 300.
+     dec: -45.
+     altitude: 153000.
+     time: '2010-01-01T00:00:00'
+     pointing:
+       ra: 180.
+       dec: 30.
+     effective_area: 1.
+  det2:
+    ra: 60.
+    dec: 10.
+    altitude: 500  # km
+    time: '2010-01-01T00:00:00'
+    pointing:
+      ra: 180.
+      dec: 30.
+    effective_area: 1.
+"""
+    f = tmp_path / "template.yaml"
+    f.write_text(text)
+    u = Universe.from_yaml(str(f))
+    assert u._seed == 12345 and list(u.detectors.keys()) == ["det3", "det2"]
+    u.explode_grb(-5.0, 10.0)
+    assert list(u.detectors.keys()) == ["det2", "det3"] and u.T0[0] == 0.0 and 0.30 < u.T0[1] < 0.40
+    sd = u.to_stan_data(-2.0, 8.0, dt=0.2, k=50)
+    assert sd["N_detectors"] == 2 and sd["counts"].shape == (2, len(np.arange(-2.0, 8.0, 0.2)) - 1) and sd["k"] == 50
+    assert sd["counts"].sum() > 2 * 500 * 9  # 500 cps of background per detector plus the burst
+    # pulse lists (several pulses per burst) are accepted by the same schema (universe.py:283-298)
+    import yaml
+
+    d = yaml.safe_load(text)
+    d["grb"].update(K=[300.0, 150.0], t_rise=[0.3, 0.6], t_decay=[2.0, 1.5], t_start=[0.0, 2.5])
+    u2 = Universe.from_dict(d)
+    u2.explode_grb(-5.0, 10.0)
+    assert len(u2.light_curves["det2"].source_arrival_times) > 100
+
+
 def test_fit_argument_routing_without_gpu(monkeypatch):
     """Fit.expected_rate picks dt / amplitude exactly like pyipn/fit.py:249-267 (checked by intercepting the ABI call)."""
     import pyipn_b200.fit as fitmod
