@@ -16,4 +16,4 @@ bench: build      ## one JSON line (needs a B200)
 	$(PY) bench.py
 
 clean:
-	rm -rf pyipn_b200/csrc/build pyipn_b200/libipn_b200.so oracle/_build
+	rm -rf pyipn_b200/csrc/build pyipn_b200/libipn_b200.so oracle/_build tests/emu/_build

@@ -8,8 +8,13 @@
 //   C_s  = sum_i [ n_i log(e_i) ] + N log B - B sum_i e_i - sum_i lgamma(n_i + 1)          (fp64, once per draw)
 // Every constant factor that multiplies a sum over ~1e5 bins is applied in fp64 (or as an fp32 hi/lo pair):
 // a single fp32 rounding of such a factor is a 6e-8 relative bias on a sum of ~5e4 nats, i.e. > 1e-3 nats.
+//
+// IPN_HOST_EMU: tests/emu/epilogue_emu.cpp compiles the arithmetic below with g++ (it supplies __device__, fmaf-exact
+// int/float bit casts and a stand-in for MUFU.LG2) so that the error budget of DESIGN.md section 3 is checked on the CPU.
 #pragma once
+#ifndef IPN_HOST_EMU
 #include "ipn_common.cuh"
+#endif
 
 namespace ipn {
 
@@ -24,6 +29,7 @@ struct DrawConst {
     float c_lo;
 };
 
+#ifndef IPN_HOST_EMU
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -34,6 +40,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 // 2^x on the FP32 pipe.  MUFU.EX2 is not usable here: measured on B200 its relative error has a MEAN of
 // -8e-9 (tools/mufu_probe.cu), and a bias b on every bin becomes b * sum_i kappa_i u_i ~ 1e-3 nats over 1e5
@@ -164,6 +171,7 @@ __device__ __forceinline__ void sincos_phase(double ph, float& s, float& c) {
     sincos_reduced_f32(rh, rl, s, c);
 }
 
+#ifndef IPN_HOST_EMU
 int prepare_bin_constants(ipn_ctx* ctx, int64_t T, const double* exposure, const int64_t* counts, double* d_binc);
 int prepare_draw_constants(ipn_ctx* ctx, int64_t S, const double* amp, const double* bkg, const double* d_binc,
                            DrawConst* d_dc);
@@ -180,5 +188,6 @@ bool tc_supported(int64_t J);
 int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
                        int64_t S, int64_t J, const double* omega, const double* a, const double* b, const DrawConst* d_dc,
                        int64_t G, const double* delays, double* ll, bool accumulate);
+#endif  // IPN_HOST_EMU
 
 }  // namespace ipn

@@ -31,6 +31,7 @@
 // IPN_TC_SKIP_MMA, IPN_TC_ONE_ISSUER, IPN_TC_EPI_DELAY, IPN_TC_GRID, IPN_TC_CHUNK_TILES (tests/test_gpu_loglik.py uses them
 // to check that results do not depend on pacing).
 #include "loglik_common.cuh"
+#include "loglik_epilogue.cuh"
 
 namespace ipn {
 
@@ -109,19 +110,7 @@ struct TcParams {
 // K-major, no swizzle: [plane][k/16][row][k%16], i.e. 8x16-byte core matrices contiguous (SBO = 128 B),
 // next 16-byte K chunk after all rows (LBO = rows * 16 B))
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_digits4(int q, int8_t& d1, int8_t& d2, int8_t& d3, int8_t& d4) {
-    int r = q;
-    const int e4 = ((r + 128) & 255) - 128;
-    r = (r - e4) >> 8;
-    const int e3 = ((r + 128) & 255) - 128;
-    r = (r - e3) >> 8;
-    const int e2 = ((r + 128) & 255) - 128;
-    r = (r - e2) >> 8;
-    d1 = (int8_t)r;
-    d2 = (int8_t)e2;
-    d3 = (int8_t)e3;
-    d4 = (int8_t)e4;
-}
+// split_digits4: loglik_epilogue.cuh
 
 // sigma / kappa of every draw: sigma = largest power of two with sigma*max|W| <= 1 and sigma*|c| <= n_crows
 __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const double* __restrict__ a,
@@ -541,98 +530,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, compensated sum.
-// HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
-template <bool HC>
-__device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                           const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                           float mks8, float& ssum, float& scomp, float& slo) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
-        // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): S2 part exact (magic-number int->float inside the FMA)
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo(xh, xl);
-        if (HC) {
-            float l;
-            v[j] = poisson_term(u, c.x, c.w, c.y, c.z, l);
-            slo += l;
-        } else {
-            v[j] = -fmaf(c.y, u, c.z * u);
-        }
-    }
-    // pairwise sum of the eight terms (|partial| <= 8 |v|), then ONE Kahan step into the running sum
-    const float g = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    const float yk = g - scomp;
-    const float tt = ssum + yk;
-    scomp = (tt - ssum) - yk;
-    ssum = tt;
-}
-
-// Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
-// not the exponent or the logarithm but three roundings of O(n)-sized quantities: n*y0, kappa*u and their difference
-// (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of eight such terms.  Here the two products and the
-// difference are formed as fp32 double-floats (exact FMA error terms, TwoSum), the small parts go to the `slo` sum, and
-// every term takes its own Kahan step.  ~11 more instructions per (delay, bin); remaining error ~3.7e-8 sqrt(sum n_i^2)
-// nats rms (measured: 1e-3 max at sum n_i^2 = 1.1e8) from the 2^(-y0) refinement of the logarithm, hence the hand-over to
-// the fp64 epilogue at sum n_i^2 = 4e7.
-template <bool HC>
-__device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                                const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                                float mks8, float& ssum, float& scomp, float& slo) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo(xh, xl);
-        // kappa u = q + (eq + klo u), q = fl(khi u)
-        const float q = c.y * u;
-        float small = fmaf(c.z, u, fmaf(c.y, u, -q));
-        float d = -q;
-        if (HC) {
-            const float w = 1.0f + u;
-            const float ew = u - (w - 1.0f);
-            const float y0 = lg2_approx(w);
-            const float tm = -y0 + kMagic;
-            const float t = exp2_core(-y0 - (tm - kMagic), tm);
-            const float r = fmaf(ew, t, fmaf(w, t, -1.0f));
-            // n log2(1 + u) = pr + (epr + nl r), pr = fl(n y0)
-            const float pr = c.x * y0;
-            const float epr = fmaf(c.x, y0, -pr);
-            d = pr - q;  // TwoSum(pr, -q)
-            const float bb = d - pr;
-            const float e1 = (pr - (d - bb)) + (-q - bb);
-            small = (fmaf(c.w, r, epr) + e1) - small;
-        } else {
-            small = -small;
-        }
-        slo += small;
-        const float yk = d - scomp;  // Kahan step per term
-        const float tt = ssum + yk;
-        scomp = (tt - ssum) - yk;
-        ssum = tt;
-    }
-}
-
-// fp64 epilogue for bright / coarsely binned data (hundreds of counts per bin): the fp32 terms above carry
-// ~6e-8 n_i relative noise each, which exceeds 1e-3 nats once sum n_i^2 is large.  4-5x slower, selected per draw.
-__device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8],
-                                                const int (&s5)[8], const float4* __restrict__ cst, double ksd, double& acc) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 c = cst[j];
-        const double x = ksd * ((double)s2[j] + 0.00390625 * (double)s3[j] +
-                                5.9604644775390625e-8 * ((double)s4[j] * 256.0 + (double)s5[j]));
-        const double u = exp2(x);
-        const double kap = (double)c.y + (double)c.z;
-        acc += (double)c.x * (log1p(u) * kLog2e) - kap * u;
-    }
-}
+// epi_units8 / epi_units8_comp / epi_units8_hifi: loglik_epilogue.cuh
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

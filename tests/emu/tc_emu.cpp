@@ -1,0 +1,361 @@
+// Host emulation of the ARITHMETIC of the tcgen05 delay-grid log-likelihood (pyipn_b200/csrc/loglik_tc.cu): test infrastructure.
+//
+// It compiles pyipn_b200/csrc/loglik_common.cuh and loglik_epilogue.cuh -- the very lines the kernel is built from -- with
+// g++ (IPN_HOST_EMU) and restates only what lives in __global__ kernels around them (operand quantisation, level sums,
+// item / warp ownership of the partial sums, fp64 fold), line by line, citing the kernel source.  Every float operation
+// is IEEE fp32 with fused fmaf exactly as on the device (compile with -ffp-contract=off; nvcc may additionally contract
+// a few `a*b + c` into FFMA, which only removes roundings).  The one thing that cannot be compiled here is MUFU.LG2:
+// `lg2_approx` below is a stand-in (correctly rounded log2 plus an injected bias and uniform noise, argv), and the
+// tests check that the result does not depend on what is injected -- which is the claim DESIGN.md section 3 makes about
+// the refinement step in poisson_term.
+//
+// Nothing of the product path runs through this file and it never touches a GPU: tests/test_emu.py builds and runs it
+// so that the error budget (1e-3 nats at 1e5 bins) is checked in the CPU suite at FULL size.
+//
+//   tc_emu funcs                          -> JSON with error statistics of exp2_poly / exp2_hilo / sincos_* / poisson_term
+//   tc_emu grid <in.bin> <bias> <noise>   -> for every delay: ll by the fp32, compensated fp32 and fp64 epilogues
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#define IPN_HOST_EMU 1
+#define __device__
+#define __forceinline__ inline
+struct float4 {
+    float x, y, z, w;
+};
+static inline float __int_as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+static inline int __float_as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
+static inline int __float2int_rn(float x) { return (int)std::nearbyintf(x); }
+
+namespace ipn {
+static double g_lg2_bias = 4e-8, g_lg2_noise = 6e-8;  // measured MUFU.LG2 on [1,2): mean +4e-8 (tools/mufu_probe.cu)
+static std::mt19937_64 g_rng(12345);
+static inline float lg2_approx(float x) {
+    if (x == 1.0f) return 0.0f;  // MUFU.LG2(1) is exactly 0 on the hardware (tools/mufu_probe.cu); tiny u relies on it
+    const double u = (double)(g_rng() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+    return (float)(std::log2((double)x) + g_lg2_bias + g_lg2_noise * u);
+}
+}  // namespace ipn
+
+#include "../../pyipn_b200/csrc/loglik_epilogue.cuh"
+
+using namespace ipn;
+
+// ---------------------------------------------------------------------------------------------------------------
+// function-level statistics
+// ---------------------------------------------------------------------------------------------------------------
+struct Stat {
+    double sum = 0, sq = 0, mx = 0;
+    long n = 0;
+    void add(double e) {
+        sum += e;
+        sq += e * e;
+        if (std::fabs(e) > mx) mx = std::fabs(e);
+        ++n;
+    }
+    void print(const char* name, bool last = false) const {
+        std::printf("\"%s\": {\"mean\": %.6e, \"rms\": %.6e, \"max\": %.6e, \"n\": %ld}%s\n", name, sum / n, std::sqrt(sq / n), mx, n,
+                    last ? "" : ",");
+    }
+};
+
+static int run_funcs() {
+    std::mt19937_64 rng(20261020);
+    auto unif = [&](double lo, double hi) { return lo + (hi - lo) * ((double)(rng() >> 11) * (1.0 / 9007199254740992.0)); };
+    Stat e_poly, e_hilo, e_sin, e_cos, e_sin_df, e_cos_df, e_log_b0, e_log_b1, e_tiny;
+    const int N = 2000000;
+    for (int i = 0; i < N; ++i) {
+        const float x = (float)unif(-30.0, 30.0);
+        e_poly.add((double)exp2_poly(x) / std::exp2((double)x) - 1.0);
+        // exp2_hilo: xh a multiple of 2^-12 (what kappa S2 is at sigma = 1), |xl| < 0.04
+        const float xh = (float)(std::nearbyint(unif(-30.0, 30.0) * 4096.0) / 4096.0);
+        const float xl = (float)unif(-0.04, 0.04);
+        e_hilo.add((double)exp2_hilo(xh, xl) / std::exp2((double)xh + (double)xl) - 1.0);
+    }
+    for (int i = 0; i < N; ++i) {
+        // phases as in the Phi image: omega t with |omega t| up to 1e5 rad
+        const double w = unif(-1000.0, 1000.0), t = unif(0.0, 100.0);
+        float s, c;
+        sincos_phase(w * t, s, c);
+        e_sin.add((double)s - std::sin(w * t));
+        e_cos.add((double)c - std::cos(w * t));
+        const double wt = w * 0.15915494309189534561;
+        const float wh = (float)wt, wl = (float)(wt - (double)wh);
+        const float th = (float)t, tl = (float)(t - (double)th);
+        if (sincos_phase_df(wh, wl, th, tl, s, c)) {
+            e_sin_df.add((double)s - std::sin(w * t));
+            e_cos_df.add((double)c - std::cos(w * t));
+        }
+    }
+    // log2(1 + u) reconstruction y0 + lo/nl: independent of the seed error
+    for (int pass = 0; pass < 2; ++pass) {
+        g_lg2_bias = pass ? -2e-7 : 4e-8;
+        g_lg2_noise = pass ? 3e-7 : 6e-8;
+        Stat& st = pass ? e_log_b1 : e_log_b0;
+        for (int i = 0; i < N; ++i) {
+            const float u = (float)std::exp2(unif(-12.0, 12.0));
+            float lo;
+            // n = 1, kappa = 0: main = y0, lo = log2e r
+            const float y0 = poisson_term(u, 1.0f, 1.44269504f, 0.0f, 0.0f, lo);
+            st.add(((double)y0 + (double)lo) - std::log2(1.0 + (double)u));
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        const float u = (float)std::exp2(unif(-60.0, -26.0));  // w == 1: the e_w term carries everything
+        float lo;
+        const float y0 = poisson_term(u, 1.0f, 1.44269504f, 0.0f, 0.0f, lo);
+        e_tiny.add(((double)y0 + (double)lo) / ((double)u * 1.4426950408889634) - 1.0);
+    }
+    std::printf("{\n");
+    e_poly.print("exp2_poly_rel");
+    e_hilo.print("exp2_hilo_rel");
+    e_sin.print("sin_phase_abs");
+    e_cos.print("cos_phase_abs");
+    e_sin_df.print("sin_phase_df_abs");
+    e_cos_df.print("cos_phase_df_abs");
+    e_log_b0.print("log2_1pu_abs_mufu_like");
+    e_log_b1.print("log2_1pu_abs_bad_seed");
+    e_tiny.print("log2_1pu_tiny_rel", true);
+    std::printf("}\n");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// grid emulation
+// ---------------------------------------------------------------------------------------------------------------
+namespace cfg {  // loglik_tc.cu namespace tc
+constexpr int TN = 32, GCOLS = 16, GROUPS = TN / GCOLS, EPI_SLOTS = 4, MIN_CROWS = 8, MAX_TILES = 4096 / TN;
+}
+
+template <class T>
+static bool rd(FILE* f, T* p, size_t n) {
+    return std::fread(p, sizeof(T), n, f) == n;
+}
+
+static int run_grid(const char* path, double bias, double noise) {
+    g_lg2_bias = bias;
+    g_lg2_noise = noise;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return 2;
+    int64_t hdr[3];
+    double ab[2];
+    if (!rd(f, hdr, 3) || !rd(f, ab, 2)) return 2;
+    const int64_t T = hdr[0], J = hdr[1], G = hdr[2];
+    const double A = ab[0], B = ab[1];
+    std::vector<double> time(T), expo(T), omega(J), a(J), b(J), delays(G);
+    std::vector<int64_t> counts(T);
+    if (!rd(f, time.data(), T) || !rd(f, expo.data(), T) || !rd(f, counts.data(), T) || !rd(f, omega.data(), J) ||
+        !rd(f, a.data(), J) || !rd(f, b.data(), J) || !rd(f, delays.data(), G))
+        return 2;
+    std::fclose(f);
+
+    // bin_const_kernel / draw_const_kernel (loglik_prep.cu)
+    double binc[4] = {0, 0, 0, 0}, sumsq = 0;
+    for (int64_t i = 0; i < T; ++i) {
+        const double n = (double)counts[i];
+        binc[0] += n;
+        if (n > 0.0) binc[1] += n * std::log(expo[i]);
+        binc[2] += expo[i];
+        binc[3] += std::lgamma(n + 1.0);
+        sumsq += n * n;
+    }
+    DrawConst dc;
+    dc.C = binc[1] + (binc[0] > 0.0 ? binc[0] * std::log(B) : 0.0) - B * binc[2] - binc[3];
+    dc.kap = B / kLn2;
+    const double c = std::log2(A / B);
+    dc.c_hi = (float)c;
+    dc.c_lo = std::isfinite(c) ? (float)(c - (double)dc.c_hi) : 0.0f;
+
+    // run_loglik_grid_tc: padded K, tiles, chunks
+    const int Kpad = (int)(((2 * J + cfg::MIN_CROWS + 31) / 32) * 32);
+    const int ncrow = Kpad - 2 * (int)J;
+    const int n_bt = (int)((T + cfg::TN - 1) / cfg::TN);
+    int nchunk = (n_bt + cfg::MAX_TILES - 1) / cfg::MAX_TILES;
+    if (nchunk < 1) nchunk = 1;
+    const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
+
+    // tc_draw_kernel: sigma, kappa, automatic epilogue mode
+    double mx = 0.0;
+    for (int j = 0; j < J; ++j) mx = std::fmax(mx, kLog2e * std::sqrt(a[j] * a[j] + b[j] * b[j]));
+    const double cabs = std::fabs((double)dc.c_hi + (double)dc.c_lo);
+    int e = 20;
+    const double lim_c = (double)ncrow * (1.0 - 1e-6);
+    while (e > -6 && (std::ldexp(mx, e) > 1.0 || (std::isfinite(cabs) && std::ldexp(cabs, e) > lim_c))) --e;
+    const float sigma_f = (float)std::ldexp(1.0, e), ks = (float)std::ldexp(1.0, -12 - e);
+    const double ysc = std::isfinite(cabs) ? std::fmax(1.0, (double)dc.c_hi) : 1.0;
+    const double crit = ysc * ysc * sumsq;
+    const int auto_mode = crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0);
+
+    // tc_perm_kernel: bins with counts first (stable)
+    std::vector<int> perm;
+    perm.reserve(T);
+    for (int64_t i = 0; i < T; ++i)
+        if (counts[i] > 0) perm.push_back((int)i);
+    const int64_t n_nz = (int64_t)perm.size();
+    for (int64_t i = 0; i < T; ++i)
+        if (!(counts[i] > 0)) perm.push_back((int)i);
+
+    // tc_pimg_kernel: Phi digit planes [3][Tpad][Kpad] and per-bin constants
+    const int64_t Tpad = (int64_t)n_bt * cfg::TN;
+    std::vector<int8_t> P((size_t)3 * Tpad * Kpad, 0);
+    std::vector<float4> cst(Tpad);
+    std::vector<float> wh(J), wl(J);
+    for (int j = 0; j < J; ++j) {
+        const double wt = omega[j] * 0.15915494309189534561;
+        wh[j] = (float)wt;
+        wl[j] = (float)(wt - (double)wh[j]);
+    }
+    const bool src = std::isfinite(dc.c_hi);
+    const bool exact_phi = std::getenv("IPN_EMU_EXACT_PHI") != nullptr;
+    for (int64_t pos = 0; pos < Tpad; ++pos) {
+        const bool valid = pos < T;
+        const int64_t i = valid ? perm[pos] : 0;
+        const double t = valid ? time[i] : 0.0;
+        const float th = (float)t, tl = (float)(t - (double)(float)t);
+        for (int k = 0; k < Kpad; k += 2) {
+            int q0 = 0, q1 = 0;
+            if (valid) {
+                if (k < 2 * J) {
+                    float sn, cn;
+                    if (exact_phi) {  // experiment (IPN_EMU_EXACT_PHI): float64 sin / cos, isolates the polynomials' share
+                        sn = (float)std::sin(omega[k >> 1] * t);
+                        cn = (float)std::cos(omega[k >> 1] * t);
+                    } else if (!sincos_phase_df(wh[k >> 1], wl[k >> 1], th, tl, sn, cn)) {
+                        sincos_phase(omega[k >> 1] * t, sn, cn);
+                    }
+                    q0 = __float2int_rn(cn * 4194304.0f);
+                    q1 = __float2int_rn(sn * 4194304.0f);
+                } else {
+                    q0 = q1 = 4194304;
+                }
+            }
+            int8_t dummy, d0[3], d1[3];
+            split_digits4(q0, dummy, d0[0], d0[1], d0[2]);
+            split_digits4(q1, dummy, d1[0], d1[1], d1[2]);
+            for (int pl = 0; pl < 3; ++pl) {
+                P[((size_t)pl * Tpad + pos) * Kpad + k] = d0[pl];
+                P[((size_t)pl * Tpad + pos) * Kpad + k + 1] = d1[pl];
+            }
+        }
+        const double kap = (valid && src) ? expo[i] * dc.kap : 0.0;
+        const float khi = (float)kap;
+        float4 cc;
+        cc.x = (valid && src) ? (float)counts[i] : 0.0f;
+        cc.y = khi;
+        cc.z = (float)(kap - (double)khi);
+        cc.w = cc.x * 1.44269504f;
+        cst[pos] = cc;
+    }
+
+    const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
+    const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
+    const double ksd = (double)ks, sigma = (double)sigma_f;
+    const double cs = (double)dc.c_hi + (double)dc.c_lo;
+
+    std::printf("{\"auto_mode\": %d, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g, \"C\": %.17g,\n\"ll\": [\n",
+                auto_mode, sigma, Kpad, (long long)n_nz, nchunk, sumsq, dc.C);
+    std::vector<int8_t> W((size_t)4 * Kpad);
+    std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
+    for (int64_t g = 0; g < G; ++g) {
+        // tc_wimg_kernel: W digit planes of this delay
+        const double dl = delays[g];
+        for (int k = 0; k < Kpad; k += 2) {
+            int q0 = 0, q1 = 0;
+            if (k < 2 * J) {
+                const int j = k >> 1;
+                const double sn = std::sin(omega[j] * dl), cn = std::cos(omega[j] * dl);
+                q0 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * cn - b[j] * sn) * sigma, -1.0), 1.0) * 1073741824.0);
+                q1 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * sn + b[j] * cn) * sigma, -1.0), 1.0) * 1073741824.0);
+            } else if (std::isfinite(cs)) {
+                const long long tot = std::llrint(cs * sigma * 1073741824.0);
+                const long long base = tot / ncrow, rem = tot - base * ncrow;
+                const int i0 = k - 2 * (int)J, i1 = i0 + 1;
+                const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
+                q0 = (int)(base + (i0 < ar ? sg : 0));
+                q1 = (int)(base + (i1 < ar ? sg : 0));
+            }
+            split_digits4(q0, W[0 * Kpad + k], W[1 * Kpad + k], W[2 * Kpad + k], W[3 * Kpad + k]);
+            split_digits4(q1, W[0 * Kpad + k + 1], W[1 * Kpad + k + 1], W[2 * Kpad + k + 1], W[3 * Kpad + k + 1]);
+        }
+        double R[3] = {0.0, 0.0, 0.0};  // per epilogue mode, the float64 atomicAdd target
+        for (int chunk = 0; chunk < nchunk; ++chunk) {
+            const int bt0 = chunk * tiles_per_chunk, bt1 = std::min(n_bt, bt0 + tiles_per_chunk);
+            // per item: one (ssum, scomp, slo) per epilogue warp of the lane quarter (slot), for each fp32 mode
+            float ssum[2][cfg::EPI_SLOTS] = {}, scomp[2][cfg::EPI_SLOTS] = {}, slo[2][cfg::EPI_SLOTS] = {};
+            double hacc[cfg::EPI_SLOTS] = {};
+            unsigned tile_seq = 0;
+            for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
+                const bool has_counts = (int64_t)bt * cfg::TN < n_nz;
+                // the nine digit-plane products of the tile (int32, exact), loglik_tc.cu header
+                for (int r = 0; r < cfg::TN; ++r) {
+                    const size_t pos = (size_t)bt * cfg::TN + r;
+                    const int8_t* p1 = &P[((size_t)0 * Tpad + pos) * Kpad];
+                    const int8_t* p2 = &P[((size_t)1 * Tpad + pos) * Kpad];
+                    const int8_t* p3 = &P[((size_t)2 * Tpad + pos) * Kpad];
+                    const int8_t *w1 = &W[0], *w2 = &W[Kpad], *w3 = &W[2 * Kpad], *w4 = &W[3 * Kpad];
+                    int s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+                    for (int k = 0; k < Kpad; ++k) {
+                        s2 += w1[k] * p1[k];
+                        s3 += w2[k] * p1[k] + w1[k] * p2[k];
+                        s4 += w3[k] * p1[k] + w2[k] * p2[k] + w1[k] * p3[k];
+                        s5 += w4[k] * p1[k] + w3[k] * p2[k] + w2[k] * p3[k];
+                    }
+                    S2[r] = s2;
+                    S3[r] = s3;
+                    S4[r] = s4;
+                    S5[r] = s5;
+                }
+                for (int cg = 0; cg < cfg::GROUPS; ++cg) {
+                    const int slot = (int)((tile_seq * cfg::GROUPS + cg) % cfg::EPI_SLOTS);
+                    for (int h = 0; h < cfg::GCOLS / 8; ++h) {
+                        const int o = cg * cfg::GCOLS + 8 * h;
+                        int t2[8], t3[8], t4[8], t5[8];
+                        for (int j = 0; j < 8; ++j) {
+                            t2[j] = S2[o + j];
+                            t3[j] = S3[o + j];
+                            t4[j] = S4[o + j];
+                            t5[j] = S5[o + j];
+                        }
+                        const float4* cp = &cst[(size_t)bt * cfg::TN + o];
+                        if (has_counts) {
+                            epi_units8<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
+                            epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
+                        } else {
+                            epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
+                            epi_units8_comp<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
+                        }
+                        epi_units8_hifi(t2, t3, t4, t5, cp, ksd, hacc[slot]);
+                    }
+                }
+            }
+            for (int s = 0; s < cfg::EPI_SLOTS; ++s) {
+                for (int m = 0; m < 2; ++m) R[m] += ((double)ssum[m][s] - (double)scomp[m][s]) + (double)slo[m][s];
+                R[2] += hacc[s];
+            }
+        }
+        // finalize_kernel
+        std::printf("[%.17g, %.17g, %.17g]%s\n", dc.C + kLn2 * R[0], dc.C + kLn2 * R[1], dc.C + kLn2 * R[2], g + 1 < G ? "," : "");
+    }
+    std::printf("]}\n");
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "funcs")) return run_funcs();
+    if (argc >= 5 && !std::strcmp(argv[1], "grid")) return run_grid(argv[2], std::atof(argv[3]), std::atof(argv[4]));
+    std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise>\n");
+    return 64;
+}
