@@ -265,8 +265,8 @@ static int run_grid(const char* path, double bias, double noise) {
     const double ksd = (double)ks, sigma = (double)sigma_f;
     const double cs = (double)dc.c_hi + (double)dc.c_lo;
 
-    std::printf("{\"auto_mode\": %d, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g, \"C\": %.17g,\n\"ll\": [\n",
-                auto_mode, sigma, Kpad, (long long)n_nz, nchunk, sumsq, dc.C);
+    std::printf("{\"auto_mode\": %d, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
+                auto_mode, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
     std::vector<int8_t> W((size_t)4 * Kpad);
     std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
     for (int64_t g = 0; g < G; ++g) {
@@ -347,7 +347,15 @@ static int run_grid(const char* path, double bias, double noise) {
             }
         }
         // finalize_kernel
-        std::printf("[%.17g, %.17g, %.17g]%s\n", dc.C + kLn2 * R[0], dc.C + kLn2 * R[1], dc.C + kLn2 * R[2], g + 1 < G ? "," : "");
+        std::printf("[");
+        for (int m = 0; m < 3; ++m) {
+            const double v = dc.C + kLn2 * R[m];
+            if (std::isfinite(v))
+                std::printf("%.17g%s", v, m < 2 ? ", " : "");
+            else  // JSON spelling python's json module accepts
+                std::printf("%s%s", std::isnan(v) ? "NaN" : (v < 0 ? "-Infinity" : "Infinity"), m < 2 ? ", " : "");
+        }
+        std::printf("]%s\n", g + 1 < G ? "," : "");
     }
     std::printf("]}\n");
     return 0;
