@@ -13,7 +13,7 @@
 // the fp32 minimax sine / cosine below.  Emulated accuracy at |phase| = 1e5 rad: max 8.5e-8, rms 1.8e-8, mean 3e-11
 // -- the same as with the fp64 reduction.  The J-term sum is a Kahan sum in fp32, folded to fp64 for the final exp.
 // Terms with |ph| >= 2^22 turns (2.6e7 rad) take an fp64 side path.
-#include "loglik_common.cuh"  // sincos_turns
+#include "rff_terms.cuh"  // rff_term, rff_term_df (sincos_turns from loglik_common.cuh)
 
 namespace ipn {
 
@@ -125,22 +125,7 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
                 const float4 f = s_f[j];
 #pragma unroll
                 for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
-                    const float ph = f.x * th[u];
-                    const float e = fmaf(f.x, th[u], -ph);
-                    const float cross = fmaf(f.x, tl[u], fmaf(f.y, th[u], e));
-                    const float k = (ph + 12582912.0f) - 12582912.0f;
-                    float sn, cs;
-                    sincos_turns(ph - k, cross, sn, cs);
-                    const float pc = f.z * cs, epc = fmaf(f.z, cs, -pc);  // a cos, exact error
-                    const float ps = f.w * sn, eps = fmaf(f.w, sn, -ps);  // b sin, exact error
-                    const float v = pc + ps;                              // TwoSum
-                    const float bb = v - pc;
-                    const float ev = (pc - (v - bb)) + (ps - bb);
-                    lo[u] += (epc + eps) + ev;
-                    const float yk = v - comp[u];  // Kahan
-                    const float t = sum[u] + yk;
-                    comp[u] = (t - sum[u]) - yk;
-                    sum[u] = t;
+                    rff_term_df(f, th[u], tl[u], sum[u], comp[u], lo[u]);
                 }
             }
 #pragma unroll
@@ -150,17 +135,7 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
                 const float4 f = s_f[j];
 #pragma unroll
                 for (int u = 0; u < RFF_BINS_PER_THREAD; ++u) {
-                    const float ph = f.x * th[u];
-                    const float e = fmaf(f.x, th[u], -ph);
-                    const float cross = fmaf(f.x, tl[u], fmaf(f.y, th[u], e));
-                    const float k = (ph + 12582912.0f) - 12582912.0f;
-                    float sn, cs;
-                    sincos_turns(ph - k, cross, sn, cs);
-                    const float v = fmaf(f.w, sn, f.z * cs);
-                    const float yk = v - comp[u];  // Kahan
-                    const float t = sum[u] + yk;
-                    comp[u] = (t - sum[u]) - yk;
-                    sum[u] = t;
+                    rff_term(f, th[u], tl[u], sum[u], comp[u]);
                 }
             }
         }

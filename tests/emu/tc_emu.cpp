@@ -14,6 +14,7 @@
 //
 //   tc_emu funcs                          -> JSON with error statistics of exp2_poly / exp2_hilo / sincos_* / poisson_term
 //   tc_emu grid <in.bin> <bias> <noise>   -> for every delay: ll by the fp32, compensated fp32 and fp64 epilogues
+//   tc_emu rff <in.bin> <out.bin>         -> rff_eval_kernel's arithmetic (rff_terms.cuh): lambda (S, T) float64 + the tier of every draw
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -51,6 +52,7 @@ static inline float lg2_approx(float x) {
 }  // namespace ipn
 
 #include "../../pyipn_b200/csrc/loglik_epilogue.cuh"
+#include "../../pyipn_b200/csrc/rff_terms.cuh"
 
 using namespace ipn;
 
@@ -361,9 +363,71 @@ static int run_grid(const char* path, double bias, double noise) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// rff_eval_kernel (rff_eval.cu): tier choice, per-bin split of tau, J-term loop, final exp
+// ---------------------------------------------------------------------------------------------------------------
+static int run_rff(const char* path, const char* out_path) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return 2;
+    int64_t hdr[3];
+    if (!rd(f, hdr, 3)) return 2;
+    const int64_t T = hdr[0], S = hdr[1], J = hdr[2];
+    std::vector<double> time(T), omega(S * J), a(S * J), b(S * J), shift(S), amp(S), out(S * T);
+    if (!rd(f, time.data(), T) || !rd(f, omega.data(), S * J) || !rd(f, a.data(), S * J) || !rd(f, b.data(), S * J) ||
+        !rd(f, shift.data(), S) || !rd(f, amp.data(), S))
+        return 2;
+    std::fclose(f);
+    std::vector<double> tiers(S);
+    std::vector<float4> sf(J);
+    for (int64_t s = 0; s < S; ++s) {
+        const double *w = &omega[s * J], *aj = &a[s * J], *bj = &b[s * J];
+        float wmax = 0.0f;
+        double q = 0.0;
+        for (int j = 0; j < J; ++j) {
+            const double wt = w[j] * 0.15915494309189534561;
+            const float wh = (float)wt;
+            sf[j] = float4{wh, (float)(wt - (double)wh), (float)aj[j], (float)bj[j]};
+            wmax = std::fmax(wmax, std::fabs(wh));
+            q += aj[j] * aj[j] + bj[j] * bj[j];
+        }
+        const float amp2 = (float)q;
+        int tier_max = 0;
+        for (int64_t i = 0; i < T; ++i) {
+            const double tau = time[i] - shift[s];
+            const float th = (float)tau, tl = (float)(tau - (double)th);
+            // the kernel decides `big` per thread over its four bins; per bin here (the fp64 path is the accurate one)
+            const bool big = !(std::fabs(th) * wmax < 4194304.0f);
+            float sum = 0.0f, comp = 0.0f, lo = 0.0f;
+            double side = 0.0;
+            int tier;
+            if (big || !(amp2 <= 100.0f)) {
+                tier = 2;
+                for (int j = 0; j < J; ++j) side = std::fma(aj[j], std::cos(w[j] * tau), std::fma(bj[j], std::sin(w[j] * tau), side));
+            } else if (amp2 > 12.0f) {
+                tier = 1;
+                for (int j = 0; j < J; ++j) rff_term_df(sf[j], th, tl, sum, comp, lo);
+                side = (double)lo;
+            } else {
+                tier = 0;
+                for (int j = 0; j < J; ++j) rff_term(sf[j], th, tl, sum, comp);
+            }
+            if (tier > tier_max) tier_max = tier;
+            out[s * T + i] = amp[s] * std::exp(((double)sum - (double)comp) + side);
+        }
+        tiers[s] = tier_max;
+    }
+    FILE* g = std::fopen(out_path, "wb");
+    if (!g) return 2;
+    std::fwrite(out.data(), sizeof(double), out.size(), g);
+    std::fwrite(tiers.data(), sizeof(double), tiers.size(), g);
+    std::fclose(g);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && !std::strcmp(argv[1], "funcs")) return run_funcs();
     if (argc >= 5 && !std::strcmp(argv[1], "grid")) return run_grid(argv[2], std::atof(argv[3]), std::atof(argv[4]));
-    std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise>\n");
+    if (argc >= 4 && !std::strcmp(argv[1], "rff")) return run_rff(argv[2], argv[3]);
+    std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise> | tc_emu rff <in.bin> <out.bin>\n");
     return 64;
 }

@@ -5,7 +5,9 @@ What this pins without a GPU: the digit-plane contraction is exact, the three ep
 fp64) meet the 1e-3 nat tolerance of BASELINE.json at BASELINE config 2's shape, the result does not depend on the error
 of the MUFU.LG2 seed, and the arg-max over the delays is the oracle's.  The GPU tests
 (tests/test_gpu_loglik.py) check the same numbers on the device; agreement of the two is the evidence that what runs on
-the tensor cores is this arithmetic and nothing else.
+the tensor cores is this arithmetic and nothing else (tools/emu_vs_device.py measured it on a B200: 5.7e-8 nats apart on
+every delay with the fp64 epilogue, profiles/r01_emu_vs_device.json).  The second half does the same for rff_eval_kernel's
+per-term arithmetic (rff_terms.cuh) against the fixtures minted from the reference's own rff.py.
 """
 import json
 import os
@@ -21,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "tc_emu.cpp")
 BUILD = os.path.join(HERE, "emu", "_build")
 EXE = os.path.join(BUILD, "tc_emu")
-HEADERS = [os.path.join(HERE, "..", "pyipn_b200", "csrc", h) for h in ("loglik_common.cuh", "loglik_epilogue.cuh")]
+HEADERS = [os.path.join(HERE, "..", "pyipn_b200", "csrc", h) for h in ("loglik_common.cuh", "loglik_epilogue.cuh", "rff_terms.cuh")]
 
 TOL_NATS = 1e-3  # BASELINE.json north_star: absolute 1e-3 nats on the log-likelihood sums
 
@@ -172,3 +174,76 @@ def test_random_ragged_shapes(emu, tmp_path):
         if kind == 0 and not inf[0] and mu.max() < 1e6:
             assert err[0] < TOL_NATS, (it, T, J, res["auto_mode"], got[0], ref[0])
     assert n_inf > 0  # the -inf branch was exercised
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rff_eval_kernel's arithmetic (pyipn_b200/csrc/rff_terms.cuh) against the fixtures minted from the reference's rff.py
+# ---------------------------------------------------------------------------------------------------------------
+RTOL_LAMBDA = 1e-6  # BASELINE.json north_star: relative 1e-6 on lambda
+
+
+def _run_rff(exe, tmp_path, time, omega, a, b, shift, amp):
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    omega, a, b = (np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64) for x in (omega, a, b))
+    S, J = omega.shape
+    src, dst = os.path.join(tmp_path, "rff_in.bin"), os.path.join(tmp_path, "rff_out.bin")
+    with open(src, "wb") as f:
+        np.array([time.size, S, J], dtype=np.int64).tofile(f)
+        for arr in (time, omega, a, b, np.broadcast_to(np.asarray(shift, dtype=np.float64), (S,)),
+                    np.broadcast_to(np.asarray(amp, dtype=np.float64), (S,))):
+            np.ascontiguousarray(arr, dtype=np.float64).tofile(f)
+    subprocess.run([exe, "rff", src, dst], check=True)
+    raw = np.fromfile(dst, dtype=np.float64)
+    return raw[:S * time.size].reshape(S, time.size), raw[S * time.size:].astype(int)
+
+
+def test_rff_arithmetic_on_the_reference_fixtures(emu, tmp_path, rff_golden):
+    """RFF / RFF_multiscale (rff.py:5-29) and the strided draw loops (fit.py:651-691): the kernel's fp32 double-float phase
+    reduction, minimax sin / cos and Kahan sum reproduce the reference's own outputs to 1e-6."""
+    from pyipn_b200.params import fold_draws
+
+    g = rff_golden
+    for scale, want in ((g["A_scale"][1], g["A_rff"]), (g["A_scale"], g["A_rff_ms"])):
+        sc = np.asarray(scale, dtype=float).reshape(-1, 1) if np.ndim(scale) else scale
+        w, a, b = fold_draws(g["A_omega1"], g["A_omega2"], g["A_beta1"], g["A_beta2"], float(g["A_bw"]), sc)
+        got, _ = _run_rff(emu, str(tmp_path), g["A_time"], w, a, b, 0.0, 1.0)
+        np.testing.assert_allclose(got[0], want, rtol=RTOL_LAMBDA)
+    for scale, want in ((g["B_scale"][1], g["B_rate_single"]), (g["B_scale"], g["B_rate_multi"])):
+        w, a, b = fold_draws(g["B_omega1"], g["B_omega2"], g["B_beta1"], g["B_beta2"], g["B_bw"], scale)
+        got, tiers = _run_rff(emu, str(tmp_path), g["B_time"], w, a, b, g["B_dt"], g["B_amp"])
+        np.testing.assert_allclose(got, want, rtol=RTOL_LAMBDA)
+    # one bin, k = 1, |phase| ~ 9e3 rad
+    w, a, b = fold_draws(g["C_omega1"], g["C_omega2"], g["C_beta1"], g["C_beta2"], 1.0, np.array([[0.4], [1.3]]))
+    got, _ = _run_rff(emu, str(tmp_path), g["C_time"], w, a, b, 0.0, 1.0)
+    np.testing.assert_allclose(got[0], g["C_rff_ms"], rtol=RTOL_LAMBDA)
+
+
+@pytest.mark.parametrize("scale,tier", [(0.15, 0), (0.45, 1), (1.5, 2)])
+def test_rff_accuracy_tiers_and_huge_phases(emu, tmp_path, scale, tier):
+    """Same cases as tests/test_gpu_rff.py: every amplitude tier, at |phase| up to 1e5 rad (sky-scale shift), holds 1e-6."""
+    from oracle import ipn_oracle as orc
+
+    rng = np.random.default_rng(int(scale * 100))
+    T, S, J = 20_000, 2, 100
+    time = 5.0e4 + np.sort(rng.uniform(0.0, 100.0, T))
+    omega = rng.normal(size=(S, J)) * np.where(np.arange(J) < J // 2, 0.05, 2.0)
+    a, b = rng.normal(size=(S, J)) * scale, rng.normal(size=(S, J)) * scale
+    shift = np.array([-1.0e3, 777.7])
+    got, tiers = _run_rff(emu, str(tmp_path), time, omega, a, b, shift, 1.0)
+    assert (tiers == tier).all(), tiers
+    for s in range(S):
+        logf = orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])
+        keep = np.abs(logf) < 600.0
+        np.testing.assert_allclose(got[s][keep], np.exp(logf[keep]), rtol=RTOL_LAMBDA)
+
+
+def test_rff_phase_beyond_the_fp32_reduction_takes_the_fp64_path(emu, tmp_path):
+    from oracle import ipn_oracle as orc
+
+    rng = np.random.default_rng(10)
+    time = np.concatenate([np.linspace(0.0, 10.0, 300), 6.0e4 + np.linspace(0, 1, 300)])
+    omega = rng.normal(size=(1, 20)) * 800.0
+    a, b = rng.normal(size=(1, 20)) * 0.1, rng.normal(size=(1, 20)) * 0.1
+    got, tiers = _run_rff(emu, str(tmp_path), time, omega, a, b, 0.0, 1.0)
+    assert tiers[0] == 2 and np.abs(omega).max() * 6.0e4 / (2 * np.pi) > 2 ** 22
+    np.testing.assert_allclose(got[0], np.exp(orc.log_intensity_folded(time, omega[0], a[0], b[0])), rtol=RTOL_LAMBDA)
