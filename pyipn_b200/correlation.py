@@ -71,6 +71,25 @@ class Correlator(object):
             fRij = self._arr_chi[i]
         return self._arr_dt[i], dTupper, fSigma
 
-    @property
-    def dt_min(self):
-        return self._dTmin
+    def info(self):
+        """correlation.py:98-125 (the summary the reference prints); returned as well as printed."""
+        dT2 = (self._idx_end_lc2 - self._idx_beg_lc2) * self.lc_2.res_ms
+        dT1 = (self._idx_end_lc1 - self._idx_beg_lc1) * self.lc_1.res_ms
+        out = "Cross-correlation info:\n"
+        out += "CC interval for lc2 (i_beg, i_end, dT): {:4d} {:4d} {:4d} ms\n".format(self._idx_beg_lc2, self._idx_end_lc2, int(dT2))
+        out += "CC interval for lc1 (i_beg, i_end, dT): {:4d} {:4d} {:4d} ms\n".format(self._idx_beg_lc1, self._idx_end_lc1, int(dT1))
+        out += "Lc scale factor: {:.3f}\n".format(self._fscale)
+        out += "Lc 1 i_start: {:d}\n".format(self._idx_lc_1)
+        out += "Lc 1 n_max: {:d}\n".format(self._n_max)
+        for i, sigma in enumerate(self._cl_sigma):
+            out += "Calculated time delay and its {:.1f} sigma CI:\n".format(sigma)
+            out += "dTcc dTcc- dTcc+: {:.3f} {:+.3f} {:+.3f}\n".format(self._dTmin, self._dTlower[i] - self._dTmin,
+                                                                      self._dTupper[i] - self._dTmin)
+        print(out)
+        return out
+
+    # correlation.py:173-187
+    dt_min = property(lambda self: self._dTmin)
+    dt_lower = property(lambda self: self._dTlower)
+    dt_upper = property(lambda self: self._dTupper)
+    f_sigma = property(lambda self: self._fSigma)

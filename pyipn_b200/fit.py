@@ -113,6 +113,18 @@ class Fit(object):
     def n_samples(self):
         return self._n_samples
 
+    # pyipn/fit.py:581-648: the posterior arrays in the reference's layout (draw = fast axis)
+    beta1 = property(lambda self: self._beta1)
+    beta2 = property(lambda self: self._beta2)
+    omega1 = property(lambda self: self._omega1)
+    omega2 = property(lambda self: self._omega2)
+    scale = property(lambda self: self._scale)
+    dt = property(lambda self: self._dt)
+    grb_theta = property(lambda self: self._grb_theta)
+    grb_phi = property(lambda self: self._grb_phi)
+    amplitude = property(lambda self: self._amplitude)
+    background = property(lambda self: self._background)
+
     def _detector_check(self, det_number):
         assert det_number in range(self._n_dets)
 

@@ -5,7 +5,10 @@ wave-front arrival ordering and ``T0`` (pyipn/universe.py:109-179), light-curve 
 seeds ``seed + 10 i`` (pyipn/universe.py:181-203, pyipn/detector.py:129-222) and ``to_stan_data``
 (pyipn/universe.py:441-529) -- the data contract the likelihood kernels consume.
 
-Not kept (out of scope): astropy frames, plotting, annuli, HDF5 save files.
+Also kept, astropy-free on km vectors: the accessors of ``GRB`` / ``Detector`` (grb.py:35-64, detector.py:34-127),
+``calculate_annulus`` / ``localize_GRB`` (universe.py:364-386, 670-697) and ``table`` (plain dicts instead of pandas).
+
+Not kept (out of scope): astropy frames, plotting, earth blockage, HDF5 save files.
 Positions come from plain spherical trigonometry (GCRS ra/dec/altitude -> km); astropy's ICRS->GCRS
 aberration terms are NOT applied, which changes T0 at the 1e-3 relative level.
 """
@@ -20,6 +23,7 @@ from .possion_gen import background_poisson_generator, source_poisson_generator
 
 C_KM_S_ASTROPY = 299792.458  # astropy.constants.c, used by the reference for T0 (universe.py:146-149)
 EARTH_RADIUS_KM = 6371.0  # geometry.py:88
+MPC_KM = 3.0856775814913673e19  # 1 Mpc in km (geometry.py:80-84 builds the GRB position in Mpc)
 
 
 def _unit_vector(ra_deg, dec_deg):
@@ -42,6 +46,18 @@ class GRB(object):
     def norm_vec(self):
         return _unit_vector(self.ra, self.dec)
 
+    @property
+    def location(self):
+        """grb.py:46: here the Cartesian position in km (the reference returns an astropy-backed GRBLocation)."""
+        return self.distance * MPC_KM * self.norm_vec
+
+    @property
+    def table(self):
+        """grb.py:50-64 as a plain dict (pandas is not a dependency of the path)."""
+        K, t_rise, t_decay, t_start = self.pulse_parameters
+        return collections.OrderedDict([("ra", self.ra), ("dec", self.dec), ("distance", self.distance), ("K", K),
+                                        ("t_rise", t_rise), ("t_decay", t_decay), ("t_start", t_start)])
+
 
 class Detector(object):
     """pyipn/detector.py:10-222 reduced to what the data path needs."""
@@ -61,6 +77,19 @@ class Detector(object):
     @property
     def pointing_vec(self):
         return _unit_vector(self.pointing_ra, self.pointing_dec)
+
+    # detector.py:34-78: the reference's accessors, astropy-free (vectors in km / unit vectors instead of SkyCoord)
+    location = property(lambda self: self.xyz_km)
+    pointing = property(lambda self: self.pointing_vec)
+    effective_area = property(lambda self: self.total_area)
+
+    def angular_separation(self, grb):
+        """detector.py:98-127 / geometry.py:24-36: angle between the pointing and the GRB direction, radians."""
+        return float(np.arccos(np.clip(np.dot(self.pointing_vec, grb.norm_vec), -1.0, 1.0)))
+
+    def light_travel_time(self, grb):
+        """detector.py:80-96: |detector - GRB| / c in seconds (c = astropy's 299792.458 km/s)."""
+        return float(np.linalg.norm(self.xyz_km - grb.location) / C_KM_S_ASTROPY)
 
     def effective_area_towards(self, grb):
         """effective_area.py:49-64: A cos(theta), zero beyond 90 degrees."""
@@ -96,6 +125,38 @@ class Universe(object):
     T0 = property(lambda self: self._T0)
     detectors = property(lambda self: self._detectors)
     light_curves = property(lambda self: self._light_curves)
+
+    @property
+    def grb_radius(self):
+        return self._grb.distance  # universe.py:87-89 (Mpc)
+
+    def calculate_annulus(self, detector1, detector2):
+        """universe.py:364-386 for two detector names: (unit connection vector, its (ra, dec) in degrees, half-opening
+        angle in radians) from the pair's T0 difference; plain km vectors instead of astropy frames."""
+        from .sky import calculate_annulus
+
+        names = list(self._detectors.keys())
+        sc_pos = np.array([d.xyz_km for d in self._detectors.values()])
+        norm_d, radec, theta = calculate_annulus(sc_pos, self._T0, names.index(detector1), names.index(detector2))
+        return norm_d, np.degrees(radec), theta
+
+    def localize_GRB(self):
+        """universe.py:670-697: least-squares intersection of all pairwise annuli; returns the solution vector."""
+        from .sky import localize_GRB
+
+        return localize_GRB(np.array([d.xyz_km for d in self._detectors.values()]), self._T0)
+
+    @property
+    def table(self):
+        """universe.py:699-734 as a plain dict of columns (pandas is not a dependency of the path)."""
+        out = collections.OrderedDict()
+        out["name"] = list(self._detectors.keys())
+        out["dt"] = None if self._T0 is None else np.asarray(self._T0)
+        out["altitude"] = [d.altitude for d in self._detectors.values()]
+        out["position"] = [f"{d.ra},{d.dec}" for d in self._detectors.values()]
+        out["pointing"] = [f"{d.pointing_ra},{d.pointing_dec}" for d in self._detectors.values()]
+        out["eff. area"] = [d.total_area for d in self._detectors.values()]
+        return out
 
     def register_detector(self, detector):
         self._detectors[detector.name] = detector

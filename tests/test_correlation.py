@@ -46,6 +46,33 @@ def test_oracle_max_sn_and_interval_match_reference(g):
         assert lo == pytest.approx(g["dTlower"][i]) and up == pytest.approx(g["dTupper"][i]) and fs == pytest.approx(g["fSigma"][i])
 
 
+def test_correlator_host_logic_without_gpu(g, monkeypatch, capsys):
+    """Everything in `Correlator` around the chi^2 scan (max-S/N window, scale factor, n_max, confidence intervals, the
+    reference's accessors and `info`, correlation.py:16-187) against the fixture, with the device call replaced by the
+    oracle's scan (host logic only; the kernel itself is checked in the GPU tests below)."""
+    import pyipn_b200.correlation as cm
+    from pyipn_b200 import BinnedLightCurve, Correlator
+
+    class Fake:
+        def correlate(self, *args):
+            r = orc.correlate(*args)
+            return r[0], r[1]
+
+    monkeypatch.setattr(cm, "default_context", lambda: Fake())
+    b1 = BinnedLightCurve(g["counts1"], g["edges1"], -10.0, 30.0, float(g["dt1"]))
+    b2 = BinnedLightCurve(g["counts2"], g["edges2"], -10.0, 30.0, float(g["dt2"]))
+    c = Correlator(b1, b2, int(g["idx_lc_1"]), int(g["idx_beg_lc2"]), int(g["idx_end_lc2"]), cl_sigma=[1, 2, 3], bkg_rate=500)
+    assert (c._idx_beg_lc1, c._idx_end_lc1, c._n_max) == (int(g["idx_beg_lc1"]), int(g["idx_end_lc1"]), int(g["n_max"]))
+    assert c.dt_min == pytest.approx(float(g["dTmin"]), abs=1e-12)
+    assert len(c.dt_lower) == len(c.dt_upper) == 3  # the reference test's own assertion (test_basic.py:92-93)
+    np.testing.assert_allclose(c.dt_lower, g["dTlower"], atol=1e-12)
+    np.testing.assert_allclose(c.dt_upper, g["dTupper"], atol=1e-12)
+    np.testing.assert_allclose(c.f_sigma, g["fSigma"], rtol=1e-10)
+    text = c.info()
+    assert "Cross-correlation info" in text and text.count("sigma CI") == 3 and "Lc 1 n_max: %d" % int(g["n_max"]) in text
+    assert capsys.readouterr().out.strip() == text.strip()
+
+
 @pytest.mark.gpu
 def test_gpu_correlate_matches_reference(ctx, g):
     from pyipn_b200 import correlate

@@ -188,3 +188,46 @@ def test_fit_argument_routing_without_gpu(monkeypatch):
     assert seen["omega"].shape == (S, 2 * k)
     with pytest.raises(AssertionError):
         fit.expected_rate(np.arange(5.0), 3)
+
+
+def test_universe_annuli_triangulation_and_accessors():
+    """calculate_annulus / localize_GRB (universe.py:364-386, 670-697) and the accessors of GRB / Detector / Fit: the true
+    direction lies on every annulus, and four detectors in general position recover it by least squares."""
+    from pyipn_b200 import Detector, Fit, GRB, Universe
+
+    grb = GRB(ra=80.0, dec=-30.0, distance=500.0, K=500.0, t_rise=0.5, t_decay=4.1)
+    u = Universe(grb, seed=7)
+    for name, ra, dec, alt in (("a", 10.0, 5.0, 500.0), ("b", 130.0, 40.0, 153000.0), ("c", 250.0, -50.0, 90000.0),
+                               ("d", 300.0, 70.0, 40000.0)):
+        u.register_detector(Detector(ra, dec, alt, 80.0, -30.0, 1.0, name))
+    u._compute_time_differences()
+    g = grb.norm_vec
+    names = list(u.detectors.keys())
+    for d1 in names:
+        for d2 in names:
+            if d1 == d2:
+                continue
+            n, radec, theta = u.calculate_annulus(d1, d2)
+            assert abs(np.dot(n, g) - np.cos(theta)) < 1e-12
+            np.testing.assert_allclose(n, [np.cos(np.radians(radec[1])) * np.cos(np.radians(radec[0])),
+                                           np.cos(np.radians(radec[1])) * np.sin(np.radians(radec[0])),
+                                           np.sin(np.radians(radec[1]))], atol=1e-12)
+    sol = u.localize_GRB()
+    np.testing.assert_allclose(sol / np.linalg.norm(sol), g, atol=1e-9)
+    # accessors
+    det = u.detectors["b"]
+    assert det.effective_area == 1.0 and np.allclose(det.pointing, g) and np.allclose(det.location, det.xyz_km)
+    assert abs(det.angular_separation(grb)) < 1e-7
+    assert 5.0e16 < det.light_travel_time(grb) < 5.2e16  # 500 Mpc in light-seconds
+    assert u.grb_radius == 500.0 and u.table["name"] == names and len(u.table["dt"]) == 4
+    assert grb.table["K"] == 500.0 and np.allclose(grb.location / np.linalg.norm(grb.location), g)
+    S, k = 3, 2
+    rng = np.random.default_rng(1)
+    arrays = dict(beta1=rng.normal(size=(k, S)), beta2=rng.normal(size=(k, S)), omega=rng.normal(size=(2, k, S)),
+                  scale=np.ones((2, S)), background=np.full((2, S), 500.0), amplitude=np.ones((1, S)), dt=np.zeros((1, S)),
+                  grb_theta=np.zeros(S), grb_phi=np.ones(S))
+    fit = Fit(**arrays)
+    for key in ("beta1", "beta2", "scale", "background", "amplitude", "dt", "grb_theta", "grb_phi"):
+        np.testing.assert_array_equal(getattr(fit, key), arrays[key])
+    np.testing.assert_array_equal(fit.omega1, arrays["omega"][0])
+    np.testing.assert_array_equal(fit.omega2, arrays["omega"][1])
