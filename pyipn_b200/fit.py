@@ -157,6 +157,35 @@ class Fit(object):
         pred_rate = self.expected_rate(mid_points, detector)
         return ppc_generator(mid_points, exposure, pred_rate, self._background_of(detector), self._n_samples, seed=seed)
 
+    # ---- the numeric halves of the reference's callers of the path (fit.py:447-579); plotting stays out of scope -------
+    def _binned(self, detector, tstart, tstop, dt):
+        self._detector_check(detector)
+        assert self._has_universe
+        lc = self._universe.light_curves[list(self._universe.light_curves.keys())[detector]]
+        rate, edges, counts = lc.get_binned_light_curve(tstart, tstop, dt)
+        return rate, edges, counts, 0.5 * (edges[:-1] + edges[1:]), np.diff(edges)
+
+    def _compute_ppcs(self, detector, tstart, tstop, dt, seed=None):
+        """fit.py:555-579: posterior-predictive counts (S, T) on the universe's light curve of ``detector``."""
+        _, _, _, mid_points, exposure = self._binned(detector, tstart, tstop, dt)
+        return self.compute_ppcs(detector, mid_points, exposure, seed=seed)
+
+    def light_curve_fit(self, detector, tstart, tstop, dt=0.2, thin=1):
+        """What plot_light_curve_fit draws (fit.py:447-484): ``(mid_points, observed rate, model rate + background)`` with
+        the model as ``(S // thin, T)``."""
+        rate, _, _, mid_points, _ = self._binned(detector, tstart, tstop, dt)
+        pred = self.expected_rate(mid_points, detector)
+        bkg = np.asarray(self._background_of(detector), dtype=np.float64)
+        return mid_points, rate, (pred + bkg[:, None])[::thin]
+
+    def light_curve_ppc_bands(self, detector, tstart, tstop, dt=0.2, levels=(99, 95, 68), seed=None):
+        """What plot_light_curve_ppcs draws (fit.py:486-553): per level the (low, high) percentile bands of the
+        posterior-predictive rate, plus the bin edges and the observed rate."""
+        rate, edges, _, _, exposure = self._binned(detector, tstart, tstop, dt)
+        ppcs = self._compute_ppcs(detector, tstart, tstop, dt, seed=seed) / exposure
+        bands = [(np.percentile(ppcs, 50.0 - lv / 2.0, axis=0), np.percentile(ppcs, 50.0 + lv / 2.0, axis=0)) for lv in levels]
+        return edges, rate, bands
+
     # ---- folded draws + north-star grids -------------------------------------------------------------------
     def folded(self):
         return fold_draws(self._omega1, self._omega2, self._beta1, self._beta2, np.ones(self._n_samples), self._scale)

@@ -231,3 +231,51 @@ def test_universe_annuli_triangulation_and_accessors():
         np.testing.assert_array_equal(getattr(fit, key), arrays[key])
     np.testing.assert_array_equal(fit.omega1, arrays["omega"][0])
     np.testing.assert_array_equal(fit.omega2, arrays["omega"][1])
+
+
+def test_fit_callers_of_the_path_without_gpu(monkeypatch):
+    """The numeric halves of plot_light_curve_fit / plot_light_curve_ppcs / _compute_ppcs (fit.py:447-579): which light
+    curve, bins, background row and draws reach the two device calls (intercepted; the oracle stands in for the device)."""
+    import pyipn_b200.fit as fitmod
+    from pyipn_b200 import Universe
+
+    d = dict(seed=3, grb=dict(ra=180.0, dec=30.0, distance=500.0, K=500.0, t_rise=0.5, t_decay=4.1),
+             detectors=dict(det3=dict(ra=300.0, dec=-45.0, altitude=153000.0, pointing=dict(ra=180.0, dec=30.0), effective_area=1.0),
+                            det2=dict(ra=60.0, dec=10.0, altitude=500.0, pointing=dict(ra=180.0, dec=30.0), effective_area=1.0)))
+    u = Universe.from_dict(d)
+    u.explode_grb(-5.0, 15.0)
+    S, k = 40, 4
+    rng = np.random.default_rng(5)
+    fit = fitmod.Fit(beta1=0.3 * rng.normal(size=(k, S)), beta2=0.3 * rng.normal(size=(k, S)), omega=rng.normal(size=(2, k, S)),
+                     scale=np.ones((2, S)), background=np.stack([np.full(S, 500.0), np.full(S, 450.0)]),
+                     amplitude=np.full((1, S), 0.8), dt=np.full((1, S), 0.34), universe=u)
+
+    class Fake:
+        def rff_eval(self, time, omega, a, b, shift, amp):
+            return np.stack([amp[s] * np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])) for s in range(len(amp))])
+
+        def poisson_counts(self, exposure, rates, bkg, seed):
+            self.seen = dict(exposure=np.array(exposure), bkg=np.array(bkg), seed=seed)
+            return np.random.default_rng(seed).poisson((rates + bkg[:, None]) * exposure).astype(np.int64)
+
+    fake = Fake()
+    monkeypatch.setattr(fitmod, "default_context", lambda: fake)
+    mid, rate, model = fit.light_curve_fit(1, -2.0, 8.0, dt=0.2, thin=4)
+    lc = u.light_curves[list(u.light_curves.keys())[1]]
+    r, edges, counts = lc.get_binned_light_curve(-2.0, 8.0, 0.2)
+    np.testing.assert_array_equal(rate, r)
+    np.testing.assert_allclose(mid, 0.5 * (edges[:-1] + edges[1:]))
+    assert model.shape == (S // 4, mid.size)
+    np.testing.assert_allclose(model[1], fit.expected_rate(mid, 1)[4] + 450.0)
+    ppcs = fit._compute_ppcs(1, -2.0, 8.0, 0.2, seed=11)
+    assert ppcs.shape == (S, mid.size) and ppcs.dtype == np.float64
+    np.testing.assert_array_equal(fake.seen["bkg"], 450.0)  # detector 1's background row
+    np.testing.assert_allclose(fake.seen["exposure"], np.diff(edges))
+    e2, r2, bands = fit.light_curve_ppc_bands(1, -2.0, 8.0, dt=0.2, levels=(95, 68), seed=11)
+    np.testing.assert_array_equal(e2, edges)
+    (lo95, hi95), (lo68, hi68) = bands
+    assert (lo95 <= lo68).all() and (lo68 <= hi68).all() and (hi68 <= hi95).all()
+    np.testing.assert_allclose(lo68, np.percentile(ppcs / np.diff(edges), 16.0, axis=0))
+    with pytest.raises(AssertionError):
+        fitmod.Fit(beta1=np.zeros((k, S)), beta2=np.zeros((k, S)), omega=np.zeros((2, k, S)), scale=np.ones(S),
+                   background=np.full(S, 500.0)).light_curve_fit(0, 0.0, 1.0)  # no universe attached
