@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--bins", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=50)
     ap.add_argument("--loglik-impl", type=int, default=0, help="0 auto, 1 FP32-pipe, 2 tcgen05")
+    ap.add_argument("--epilogue", type=int, default=0,
+                    help="IPN_OPT_HIFI of the tcgen05 path: 0 auto (default), 1 fp64, 2 fp32, 3 compensated fp32, 4 product (opt-in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -143,7 +145,7 @@ def main():
     import torch.distributed as dist
 
     from pyipn_b200 import Context
-    from pyipn_b200._lib import OPT_LOGLIK_IMPL
+    from pyipn_b200._lib import OPT_HIFI, OPT_LOGLIK_IMPL
     from pyipn_b200.distributed import gather_columns, shard_bounds
     from pyipn_b200.synth import delay_grid_workload
 
@@ -168,6 +170,8 @@ def main():
     ctx = Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option(OPT_LOGLIK_IMPL, a.loglik_impl)
+    if a.epilogue:
+        ctx.set_option(OPT_HIFI, a.epilogue)
 
     def step_resident():
         flush.zero_()
@@ -297,7 +301,8 @@ def main():
             "dtype": "int8 digit planes -> int32 (exact) + f32 epilogue, f64 phases/reduction" if impl == 2 else "f32 contraction, f64 phases/reduction",
             "data": "synthetic",
             "config": {"workload": workload_name(a, world), "l2": "256 MiB memset between steps, inside the timed region",
-                       "loglik_impl": {0: "auto", 1: "fp32-pipe", 2: "tcgen05"}[a.loglik_impl] + f" -> ran {impl}", "seed": 20261019},
+                       "loglik_impl": {0: "auto", 1: "fp32-pipe", 2: "tcgen05"}[a.loglik_impl] + f" -> ran {impl}", "seed": 20261019,
+                       **({"epilogue": a.epilogue} if a.epilogue else {})},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": units_step * a.steps / e2e_s, "unit": "grid-point*bins/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "timer": "host perf_counter, max over ranks", "matches_resident": same},

@@ -59,7 +59,7 @@ struct ipn_ctx {
     // options
     int loglik_impl = 0;
     int precise_w = 1;
-    int hifi_mode = 0;  // tcgen05 path epilogue: 0 auto, 1 force fp64, 2 force plain fp32, 3 force compensated fp32
+    int hifi_mode = 0;  // tcgen05 path epilogue: 0 auto, 1 force fp64, 2 force plain fp32, 3 force compensated fp32, 4 auto + product
     int64_t draw_batch = 0;
     // scratch
     ipn::Scratch wtab;     // delay tables of the current draw batch

@@ -85,7 +85,7 @@ constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224)
 struct TcDraw {
     float ks;     // kappa = 2^-12 / sigma
     float sigma;  // power of two
-    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64
+    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64, 3 product (EPI_* below)
     int pad;
 };
 
@@ -140,6 +140,9 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
     const double crit = ysc * ysc * sumsq;
     t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0))));
+    // flags[1] = 4 (opt-in, IPN_OPT_HIFI = 4): the product epilogue (EPI_PROD, loglik_epilogue.cuh) for the draws the plain
+    // fp32 epilogue would get; the others keep the automatic choice.
+    if (flags[1] == 4 && t.hifi == 0) t.hifi = 3;
     t.pad = 0;
     td[sl] = t;
 }
@@ -289,13 +292,122 @@ __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t*
     if (i < T) perm[flag ? nz_before : (int64_t)s_total + (i - nz_before)] = (int)i;
 }
 
+// Count-sorted variant of the permutation for the product epilogue (IPN_OPT_HIFI = 4): bins with one count first, then
+// two, three, four-or-more, and the empty bins last, each class in its original order (a stable counting sort over five
+// classes, same two passes and the same outputs as above).  Nearly every 32-bin tile then holds ONE count value, which
+// tc_pimg_kernel records in the tile's flag block, and the epilogue multiplies (1 + u) that many times in straight-line code.
+__device__ __forceinline__ int count_class(int64_t n) { return n <= 0 ? 4 : (n >= 4 ? 3 : (int)n - 1); }
+
+__global__ void __launch_bounds__(1024) tc_perm_sorted_count_kernel(int64_t T, const int64_t* __restrict__ counts,
+                                                                    int* __restrict__ blk_cnt4, double* __restrict__ blk_sq) {
+    __shared__ int wsum[4][32];
+    __shared__ double wsq[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + tid;
+    const int64_t ni = (i < T) ? counts[i] : 0;
+    const int cls = count_class(ni);
+    double sq = (double)ni * (double)ni;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = __popc(__ballot_sync(0xffffffffu, cls == k));
+        if (lane == 0) wsum[k][warp] = c;
+    }
+    if (lane == 0) wsq[warp] = sq;
+    __syncthreads();
+    if (tid < 4) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += wsum[tid][w];
+        blk_cnt4[blockIdx.x * 4 + tid] = t;
+    }
+    if (tid == 0) {
+        double q = 0.0;
+        for (int w = 0; w < 32; ++w) q += wsq[w];
+        blk_sq[blockIdx.x] = q;
+    }
+}
+
+__global__ void __launch_bounds__(1024) tc_perm_sorted_kernel(int64_t T, const int64_t* __restrict__ counts, int n_blk,
+                                                              const int* __restrict__ blk_cnt4, const double* __restrict__ blk_sq,
+                                                              int* __restrict__ perm, int* __restrict__ n_nz_out, int hifi_mode) {
+    __shared__ int s_before[4], s_total[4];  // bins of class k in the blocks before this one / in all blocks
+    __shared__ int wcnt[4][32];              // bins of class k in each warp of this block
+    __shared__ double s_sq;
+    __shared__ int wred[8][32];
+    __shared__ double wsq[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        // per class: bins in the blocks before this one, and in all blocks (integer sums: exact, order-independent)
+        int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [k] = before, [4 + k] = total
+        double sq = 0.0;
+        for (int b = tid; b < n_blk; b += 1024) {
+            const int* c = blk_cnt4 + (size_t)b * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[4 + k] += c[k];
+                if (b < (int)blockIdx.x) acc[k] += c[k];
+            }
+            sq += blk_sq[b];  // integers below 2^53: exact as well
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int x = acc[q];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) wred[q][warp] = x;
+        }
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) wsq[warp] = sq;
+        __syncthreads();
+        if (tid < 8) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += wred[tid][w];
+            if (tid < 4) s_before[tid] = t; else s_total[tid - 4] = t;
+        }
+        if (tid == 32) {
+            double q = 0.0;
+            for (int w = 0; w < 32; ++w) q += wsq[w];
+            s_sq = q;
+        }
+    }
+    const int64_t i = (int64_t)blockIdx.x * 1024 + tid;
+    const int cls = (i < T) ? count_class(counts[i]) : 4;
+    int rank = 0;  // bins of my class before me in my warp
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+        if (lane == 0) wcnt[k][warp] = __popc(m);
+        if (cls == k) rank = __popc(m & ((1u << lane) - 1u));
+    }
+    const unsigned mnz = __ballot_sync(0xffffffffu, cls != 4);
+    const int nz_lane = __popc(mnz & ((1u << lane) - 1u));  // bins with counts before me in my warp
+    __syncthreads();
+    const int n_nz = s_total[0] + s_total[1] + s_total[2] + s_total[3];
+    if (blockIdx.x == 0 && tid == 0) {
+        n_nz_out[0] = n_nz;
+        n_nz_out[1] = hifi_mode;
+        *reinterpret_cast<double*>(n_nz_out + 2) = s_sq;  // sum n_i^2, read by tc_draw_kernel for the per-draw epilogue choice
+    }
+    if (i >= T) return;
+    if (cls < 4) {
+        int pos = s_before[cls] + rank;
+        for (int k = 0; k < cls; ++k) pos += s_total[k];         // classes sorted before mine
+        for (int w = 0; w < warp; ++w) pos += wcnt[cls][w];      // my class in the warps before mine
+        perm[pos] = (int)i;
+    } else {
+        int nz_before = s_before[0] + s_before[1] + s_before[2] + s_before[3] + nz_lane;
+        for (int w = 0; w < warp; ++w) nz_before += wcnt[0][w] + wcnt[1][w] + wcnt[2][w] + wcnt[3][w];
+        perm[(int64_t)n_nz + (i - nz_before)] = (int)i;
+    }
+}
+
 // Phi digit planes + Poisson constants of one (draw, tile of 64 permuted bins).
 // 256 threads: row = tid % 32, eight threads per row interleave the 16-wide K chunks.
 __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
                                                       const double* __restrict__ exposure, const int64_t* __restrict__ counts,
                                                       const int* __restrict__ perm, const int* __restrict__ n_nz,
                                                       const double* __restrict__ omega, const DrawConst* __restrict__ dc,
-                                                      int n_bt, uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
+                                                      const TcDraw* __restrict__ td, int n_bt, uint32_t b_bytes, uint32_t b_plane,
+                                                      uint8_t* __restrict__ Pimg) {
     const int row = threadIdx.x & (tc::TN - 1);
     const int kg = threadIdx.x / tc::TN;
     const int bt = blockIdx.x;
@@ -351,11 +463,22 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
         c.y = khi;
         c.z = (float)(kap - (double)khi);
         c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
+        float n_uniform = 0.0f;
+        if (td[sl].hifi == 3) {
+            // product epilogue: n as an integer, and in the tile's flag block the count value all its bins share (1, 2 or 3;
+            // 0 = mixed, four or more, or padding: the epilogue then loops per bin).  The threads here are rows 0 .. TN - 1.
+            const int n_int = (valid && src) ? (int)min(counts[i], (int64_t)0x7fffffff) : 0;
+            c.w = __int_as_float(n_int);
+            const unsigned act = __activemask();
+            const int n0 = __shfl_sync(act, n_int, 0);
+            if (__all_sync(act, n_int == n0) && n0 >= 1 && n0 <= 3) n_uniform = (float)n0;
+        }
         *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
         if (row == 0) {
             float4 f;
             f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
-            f.y = f.z = f.w = 0.0f;
+            f.y = n_uniform;
+            f.z = f.w = 0.0f;
             *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)tc::TN * 16) = f;
         }
     }
@@ -544,7 +667,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // One instantiation per epilogue mode (EPI_FP32 / EPI_COMP / EPI_FP64): each handles only the draws flagged for its mode
 // (every role skips the others' items), so the common fp32 instantiation carries no compensated or fp64 code in its
 // instruction-cache footprint.
-enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2 };
+enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, EPI_PROD = 3 };
 template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
@@ -754,6 +877,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
+            double pP = 1.0;  // EPI_PROD: running product 2^pE pP of (1 + u)^n over the item's bins
+            int pE = 0;
             double hacc = 0.0;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
@@ -767,6 +892,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 tc_fence_after();
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
+                const float n_uniform = cbase[TN].y;  // EPI_PROD: the count value all bins of the tile share, 0 = none
                 for (; cg < GROUPS; cg += EPI_SLOTS) {
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
@@ -810,6 +936,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                         for (int h = 0; h < NH; ++h) {
                             if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
+                            else if (MODE == EPI_PROD) {
+#define IPN_PROD_UNITS(NU) epi_units8_prod<NU>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, pP, pE)
+                                if (!has_counts) IPN_PROD_UNITS(0);
+                                else if (n_uniform == 1.0f) IPN_PROD_UNITS(1);
+                                else if (n_uniform == 2.0f) IPN_PROD_UNITS(2);
+                                else if (n_uniform == 3.0f) IPN_PROD_UNITS(3);
+                                else IPN_PROD_UNITS(-1);
+#undef IPN_PROD_UNITS
+                            }
                             else if (MODE == EPI_COMP && has_counts)
                                 epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
@@ -824,7 +959,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     if (lane == 0) mbar_arrive(c_empty + cs);
                 }
             }
-            const double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
+            double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
+            if (MODE == EPI_PROD) acc += (double)pE + log2(pP);  // the item's one logarithm
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
         }
@@ -873,40 +1009,47 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     if ((rc = ctx->tcdraw.ensure((size_t)Sbatch * sizeof(TcDraw)))) return rc;
     const int n_pblk = (int)((T + 1023) / 1024);
     const size_t perm_ints = (((size_t)T + 8 + 1) / 2) * 2;  // flags + permutation, padded so the doubles behind stay aligned
-    if ((rc = ctx->perm.ensure(perm_ints * sizeof(int) + (size_t)(n_pblk + 1) * (sizeof(double) + sizeof(int)) + 64))) return rc;
+    if ((rc = ctx->perm.ensure(perm_ints * sizeof(int) + (size_t)(n_pblk + 1) * (sizeof(double) + 4 * sizeof(int)) + 64))) return rc;
     int* d_nnz = ctx->perm.as<int>();  // [0] n_nz, [1] mode, [2..3] sum n^2 as double (8-byte aligned)
     int* d_perm = d_nnz + 8;
     double* d_blk_sq = reinterpret_cast<double*>(d_nnz + perm_ints);
     int* d_blk_cnt = reinterpret_cast<int*>(d_blk_sq + n_pblk + 1);
-    if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
-    tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm, d_nnz,
-                                                                    ctx->hifi_mode);  // T == 0: only writes the flags
+    if (ctx->hifi_mode == 4) {  // product epilogue: bins ordered by their counts (d_blk_cnt holds four counters per block)
+        if (n_pblk > 0) tc_perm_sorted_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
+        tc_perm_sorted_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm,
+                                                                               d_nnz, ctx->hifi_mode);
+    } else {
+        if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
+        tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm, d_nnz,
+                                                                        ctx->hifi_mode);  // T == 0: only writes the flags
+    }
     ctx->launches += n_pblk > 0 ? 2 : 1;
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
     uint8_t* d_P = ctx->misc.as<uint8_t>();
     double* d_R = ctx->accum.as<double>();
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
-    void (*kern[3])(const TcParams) = {nullptr, nullptr, nullptr};  // by epilogue mode
+    void (*kern[4])(const TcParams) = {nullptr, nullptr, nullptr, nullptr};  // by epilogue mode
     switch (ksteps) {
 #define IPN_TC_CASE(K)                            \
     case K:                                       \
         kern[0] = loglik_tc_kernel<K, EPI_FP32>;  \
         kern[1] = loglik_tc_kernel<K, EPI_COMP>;  \
         kern[2] = loglik_tc_kernel<K, EPI_FP64>;  \
+        kern[3] = loglik_tc_kernel<K, EPI_PROD>;  \
         break;
         IPN_TC_CASE(1) IPN_TC_CASE(2) IPN_TC_CASE(3) IPN_TC_CASE(4) IPN_TC_CASE(5) IPN_TC_CASE(6)
         default: IPN_TC_CASE(7)
 #undef IPN_TC_CASE
     }
     // which instantiations can have work: auto -> fp32, compensated and (rarely) fp64; forced modes -> one
-    const bool run_mode[3] = {ctx->hifi_mode == 0 || ctx->hifi_mode == 2, ctx->hifi_mode == 0 || ctx->hifi_mode == 3,
-                              ctx->hifi_mode == 0 || ctx->hifi_mode == 1};
+    const int hm = ctx->hifi_mode;  // 4 = product epilogue where it applies, the automatic choice elsewhere
+    const bool run_mode[4] = {hm == 0 || hm == 2 || hm == 4, hm == 0 || hm == 3 || hm == 4, hm == 0 || hm == 1 || hm == 4, hm == 4};
     {
         int* trap = trap_record_device_ptr();
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int m = 0; m < 3; ++m)
+    for (int m = 0; m < 4; ++m)
         IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
@@ -917,7 +1060,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                                                                             n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
             tc_pimg_kernel<<<dim3(n_bt, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
-                                                                     omega, d_dc, n_bt, b_bytes, b_plane, d_P);
+                                                                     omega, d_dc, d_td, n_bt, b_bytes, b_plane, d_P);
         ctx->launches += 3;
         IPN_CUDA_CHECK(cudaGetLastError());
 
@@ -959,7 +1102,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                 p.dbg = ctx->dbg.as<unsigned long long>();
             }
             main_kernel_begin(ctx);
-            for (int m = 0; m < 3; ++m) {
+            for (int m = 0; m < 4; ++m) {
                 if (!run_mode[m]) continue;
                 // the per-draw modes are decided on the device, so in auto mode all three are launched; an instantiation
                 // without draws of its mode exits at once (~15 us)

@@ -38,7 +38,7 @@ def emu():
     return EXE
 
 
-def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, counts=None):
+def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, counts=None, prod=False):
     counts = w["counts"] if counts is None else counts
     amp = float(w["amp"][s]) if amp is None else amp
     path = os.path.join(tmp_path, "in.bin")
@@ -48,7 +48,8 @@ def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, coun
         for arr, dt in ((w["time"], np.float64), (w["exposure"], np.float64), (counts, np.int64), (w["omega"][s], np.float64),
                         (w["a"][s], np.float64), (w["b"][s], np.float64), (delays, np.float64)):
             np.ascontiguousarray(arr, dtype=dt).tofile(f)
-    out = subprocess.run([exe, "grid", path, repr(bias), repr(noise)], check=True, capture_output=True, text=True).stdout
+    cmd = [exe, "gridprod", path] if prod else [exe, "grid", path, repr(bias), repr(noise)]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     res = json.loads(out)
     ref = corc.loglik_delay_grid(counts, w["time"], w["exposure"], w["omega"][s:s + 1], w["a"][s:s + 1], w["b"][s:s + 1],
                                  [amp], w["bkg"][s:s + 1], delays)[:, 0]
@@ -247,3 +248,50 @@ def test_rff_phase_beyond_the_fp32_reduction_takes_the_fp64_path(emu, tmp_path):
     got, tiers = _run_rff(emu, str(tmp_path), time, omega, a, b, 0.0, 1.0)
     assert tiers[0] == 2 and np.abs(omega).max() * 6.0e4 / (2 * np.pi) > 2 ** 22
     np.testing.assert_allclose(got[0], np.exp(orc.log_intensity_folded(time, omega[0], a[0], b[0])), rtol=RTOL_LAMBDA)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# product epilogue (IPN_OPT_HIFI = 4, opt-in until measured on the device): count-sorted bins, one logarithm per work item
+# ---------------------------------------------------------------------------------------------------------------
+def test_product_epilogue_full_size(emu, tmp_path):
+    """BASELINE config 2 shape through the product pipeline (count-sorted permutation, per-tile count flags, float64
+    running product): closer to the oracle than the per-bin logarithm it replaces, same arg-max."""
+    w = synth.delay_grid_workload(T=100_000, G=4096, S=1)
+    g_true = int(np.argmin(np.abs(w["delays"] - w["true_delay"])))
+    idx = np.unique(np.concatenate([np.arange(g_true - 4, g_true + 5), [0, 511, 1777, 3000, 4095]]))
+    res, llp, ref = _run_grid(emu, str(tmp_path), w, 0, w["delays"][idx], prod=True)
+    assert res["prod_mode"] == 3
+    err = llp[:, 0] - ref
+    assert np.abs(err).max() < 4e-4 and np.sqrt(np.mean(err ** 2)) < 2.5e-4, err
+    assert idx[np.argmax(llp[:, 0])] == idx[np.argmax(ref)]
+
+
+def test_product_epilogue_count_classes_and_edges(emu, tmp_path):
+    """Bins with 0 ... 40 counts (all five count classes, the per-bin loop, tiles across class boundaries), ragged T, zero
+    exposures, a tiny source (u ~ 1e-9: fl32(1 + u) = 1, the float64 product must keep it) and amp = 0."""
+    rng = np.random.default_rng(7)
+    for T, bright in ((1000 + 17, 1.0), (333, 30.0), (64, 1.0), (5, 1.0)):
+        w = synth.delay_grid_workload(T=T, G=8, S=1, bkg=500.0 * bright, boost=400.0 * bright)
+        d = w["delays"][[0, 5]]
+        _, llp, ref = _run_grid(emu, str(tmp_path), w, 0, d, prod=True)
+        assert np.abs(llp[:, 0] - ref).max() < 2e-4 * bright, (T, bright, llp[:, 0] - ref)
+    w = synth.delay_grid_workload(T=4000, G=8, S=1)
+    d = w["delays"][[1, 6]]
+    for amp in (4e-7, 0.0):  # u ~ 1e-9 everywhere; background only
+        _, llp, ref = _run_grid(emu, str(tmp_path), w, 0, d, amp=amp, prod=True)
+        assert np.abs(llp[:, 0] - ref).max() < 2e-5, (amp, llp[:, 0] - ref)
+        _, ll, _ = _run_grid(emu, str(tmp_path), w, 0, d, amp=amp)
+        assert np.abs(ll[:, 0] - ref).max() < 2e-5
+    # the source term itself (ll - ll(amp = 0)) of the tiny source is resolved, not rounded away
+    _, lt, rt = _run_grid(emu, str(tmp_path), w, 0, d, amp=4e-7, prod=True)
+    _, l0, r0 = _run_grid(emu, str(tmp_path), w, 0, d, amp=0.0, prod=True)
+    np.testing.assert_allclose(lt[:, 0] - l0[:, 0], rt - r0, rtol=5e-2, atol=1e-9)
+    assert np.abs(rt - r0).max() > 1e-8
+    # counts in a bin of zero exposure: -inf from the constant term, whatever the epilogue
+    cz = w["counts"].copy()
+    ez = w["exposure"].copy()
+    ez[10] = 0.0
+    cz[10] = 3
+    wz = dict(w, exposure=ez, counts=cz)
+    _, llz, refz = _run_grid(emu, str(tmp_path), wz, 0, d, prod=True)
+    assert np.isneginf(refz).all() and np.isneginf(llz[:, 0]).all()
