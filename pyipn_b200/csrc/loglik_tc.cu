@@ -1050,7 +1050,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
     for (int m = 0; m < 4; ++m)
-        IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (run_mode[m]) IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
