@@ -79,6 +79,13 @@ __device__ __forceinline__ float exp2_hilo(float xh, float xl) {
     return exp2_core((xh - (t - kMagic)) + xl, t);
 }
 
+// The same without the clamps, for callers that have bounded the exponent themselves (|xh + xl| <= 120: the product
+// epilogue is only selected for draws with |c| + log2e sum_j |(a_j, b_j)| <= 120, tc_draw_kernel).
+__device__ __forceinline__ float exp2_hilo_bounded(float xh, float xl) {
+    const float t = xh + kMagic;
+    return exp2_core((xh - (t - kMagic)) + xl, t);
+}
+
 // One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u  as a main part (ONE rounding of the
 // exact n y0 - kappa u) plus a small correction `lo` that the caller sums separately in fp32:
 //   w = fl(1 + u),  e_w = (1 + u) - w  recovered exactly (Fast2Sum; valid for every u < 2^24),

@@ -60,7 +60,8 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
 // float64 is what makes it this short: 53 bits keep a u as small as 1e-16 (the tiny-source regime, where fl32(1 + u) = 1
 // would drop the source altogether), the rounding of the product is negligible (what remains is the 2.6e-8 rms of 2^x,
 // random, i.e. ~1e-5 nats over 1e5 bins), and the exponent range lets several multiplications pass between
-// renormalisations: u <= 2^120 (exp2_hilo clamps), at most six multiplications un-renormalised in a row -> P < 2^722.
+// renormalisations: u <= 2^120 (the mode is only selected for draws whose exponent is bounded by 120 -- which also lets
+// 2^x drop its clamps), at most six multiplications un-renormalised in a row -> P < 2^722.
 // Renormalisation: E += exponent(P), exponent field of P reset to 0 -- three integer instructions.
 // The counts of a bin are warp-uniform (one bin per TMEM column, one delay per lane), so the loop over the second, third ...
 // count does not diverge.
@@ -106,7 +107,7 @@ __device__ __forceinline__ void epi_units8_prod(const int (&s2)[8], const int (&
         const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
         float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
         xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo(xh, xl);
+        const float u = exp2_hilo_bounded(xh, xl);  // |x| <= 120 by selection (tc_draw_kernel)
         v[j] = -fmaf(c.y, u, c.z * u);
         if (NU > 0) {
             // u <= 2^120: NU <= 3 multiplications per bin and a renormalisation every second bin keep P < 2^722

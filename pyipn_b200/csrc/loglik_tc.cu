@@ -119,10 +119,12 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     const int sl = blockIdx.x * blockDim.x + threadIdx.x;
     if (sl >= Sb) return;
     const int64_t s = S0 + sl;
-    double mx = 0.0;
+    double mx = 0.0, sumw = 0.0;
     for (int j = 0; j < J; ++j) {
         const double aj = a[s * J + j], bj = b[s * J + j];
-        mx = fmax(mx, kLog2e * sqrt(aj * aj + bj * bj));
+        const double wj = kLog2e * sqrt(aj * aj + bj * bj);
+        mx = fmax(mx, wj);
+        sumw += wj;
     }
     const double c = fabs((double)dc[s].c_hi + (double)dc[s].c_lo);  // inf for amp == 0 (handled through the consts)
     int e = 20;  // sigma = 2^e, start high and walk down
@@ -141,8 +143,10 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     const double crit = ysc * ysc * sumsq;
     t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0))));
     // flags[1] = 4 (opt-in, IPN_OPT_HIFI = 4): the product epilogue (EPI_PROD, loglik_epilogue.cuh) for the draws the plain
-    // fp32 epilogue would get; the others keep the automatic choice.
-    if (flags[1] == 4 && t.hifi == 0) t.hifi = 3;
+    // fp32 epilogue would get, provided no exponent can leave [-120, 120] (|x| <= |c| + log2e sum_j |(a_j, b_j)|, the phases
+    // of all frequencies aligned; ~40 for a draw of the prior): that epilogue evaluates 2^x without clamps.  The other
+    // draws keep the automatic choice.
+    if (flags[1] == 4 && t.hifi == 0 && (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0) t.hifi = 3;
     t.pad = 0;
     td[sl] = t;
 }

@@ -191,8 +191,12 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
     const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
 
     // tc_draw_kernel: sigma, kappa, automatic epilogue mode
-    double mx = 0.0;
-    for (int j = 0; j < J; ++j) mx = std::fmax(mx, kLog2e * std::sqrt(a[j] * a[j] + b[j] * b[j]));
+    double mx = 0.0, sumw = 0.0;
+    for (int j = 0; j < J; ++j) {
+        const double wj = kLog2e * std::sqrt(a[j] * a[j] + b[j] * b[j]);
+        mx = std::fmax(mx, wj);
+        sumw += wj;
+    }
     const double cabs = std::fabs((double)dc.c_hi + (double)dc.c_lo);
     int e = 20;
     const double lim_c = (double)ncrow * (1.0 - 1e-6);
@@ -201,7 +205,9 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
     const double ysc = std::isfinite(cabs) ? std::fmax(1.0, (double)dc.c_hi) : 1.0;
     const double crit = ysc * ysc * sumsq;
     const int auto_mode = crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0);
-    const int prod_mode = auto_mode == 0 ? 3 : auto_mode;  // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run
+    // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run and no exponent can leave [-120, 120]
+    const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
+    const int prod_mode = (auto_mode == 0 && xmax <= 120.0) ? 3 : auto_mode;
 
     // tc_perm_kernel: bins with counts first (stable); tc_perm_sorted_kernel (product epilogue): by count class 1, 2, 3, >= 4, 0
     std::vector<int> perm;
@@ -285,8 +291,8 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
     const double ksd = (double)ks, sigma = (double)sigma_f;
     const double cs = (double)dc.c_hi + (double)dc.c_lo;
 
-    std::printf("{\"auto_mode\": %d, \"prod_mode\": %d, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
-                auto_mode, prod_mode, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
+    std::printf("{\"auto_mode\": %d, \"prod_mode\": %d, \"xmax\": %.6g, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
+                auto_mode, prod_mode, xmax, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
     std::vector<int8_t> W((size_t)4 * Kpad);
     std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
     for (int64_t g = 0; g < G; ++g) {

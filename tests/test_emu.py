@@ -295,3 +295,14 @@ def test_product_epilogue_count_classes_and_edges(emu, tmp_path):
     wz = dict(w, exposure=ez, counts=cz)
     _, llz, refz = _run_grid(emu, str(tmp_path), wz, 0, d, prod=True)
     assert np.isneginf(refz).all() and np.isneginf(llz[:, 0]).all()
+
+
+def test_product_epilogue_is_not_selected_beyond_its_exponent_bound(emu, tmp_path):
+    """The product epilogue evaluates 2^x without clamps: tc_draw_kernel only selects it when |c| + log2e sum_j |(a_j, b_j)|
+    <= 120 (a draw of the prior: ~40); four times the amplitudes and the draw keeps the automatic choice."""
+    w = synth.delay_grid_workload(T=2000, G=8, S=1)
+    res, _, _ = _run_grid(emu, str(tmp_path), w, 0, w["delays"][:1], prod=True)
+    assert res["prod_mode"] == 3 and res["xmax"] < 60
+    big = dict(w, a=4.0 * w["a"], b=4.0 * w["b"])
+    res, _, _ = _run_grid(emu, str(tmp_path), big, 0, w["delays"][:1], prod=True)
+    assert res["xmax"] > 120 and res["prod_mode"] == res["auto_mode"]
