@@ -54,7 +54,6 @@ def test_thinning_matches_intensity_and_host_generator(ctx):
 def test_device_data_path_events_to_likelihood(ctx):
     """events (GPU thinning) -> counts (GPU histogram) -> delay-grid likelihood (GPU), recovered delay."""
     from pyipn_b200 import LightCurve
-    from pyipn_b200.params import fold_draws
     from pyipn_b200.possion_gen import background_poisson_generator_gpu, source_poisson_generator_gpu
 
     lag = 0.4

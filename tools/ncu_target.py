@@ -1,6 +1,5 @@
 """Short single-GPU run for ncu: one delay-grid call at the bench shape with a handful of draws."""
 import sys
-import numpy as np
 sys.path.insert(0, ".")
 from pyipn_b200 import Context
 from pyipn_b200._lib import OPT_LOGLIK_IMPL

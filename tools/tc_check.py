@@ -1,5 +1,5 @@
 """Correctness probe of the tcgen05 path against the oracle (small shapes first; bounded by `timeout`)."""
-import json, sys, time
+import json, sys
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import ipn_oracle as orc

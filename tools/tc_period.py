@@ -1,7 +1,6 @@
 """Per-tile cycle budget of the tcgen05 likelihood kernel: `IPN_TC_DEBUG=1 python tools/tc_period.py S` prints the mean
 cycles per tile and the barrier waits of each role (needs a B200).  IPN_TC_SKIP_MATH / IPN_TC_SKIP_MMA isolate the roles."""
 import sys
-import numpy as np
 sys.path.insert(0, ".")
 from pyipn_b200 import Context
 from pyipn_b200._lib import OPT_HIFI
