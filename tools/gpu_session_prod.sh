@@ -17,6 +17,7 @@ for name in ("default", "prod"):
     except Exception as e:  # noqa: BLE001
         print(name, "no result:", e)
 PY
+for m in 2 4; do IPN_TC_DEBUG=1 timeout 120 python tools/tc_period.py 64 $m > gpurun_out/tc_period_$m.log 2>&1; tail -2 gpurun_out/tc_period_$m.log; done
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --epilogue 4"
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:loglik_tc_kernelILi7ELi3 -s 2 -c 1 \
     -o gpurun_out/prof_prod $CMD > gpurun_out/ncu_prod.log 2>&1
