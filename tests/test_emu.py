@@ -306,3 +306,28 @@ def test_product_epilogue_is_not_selected_beyond_its_exponent_bound(emu, tmp_pat
     big = dict(w, a=4.0 * w["a"], b=4.0 * w["b"])
     res, _, _ = _run_grid(emu, str(tmp_path), big, 0, w["delays"][:1], prod=True)
     assert res["xmax"] > 120 and res["prod_mode"] == res["auto_mode"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the bin-permutation kernels themselves (pyipn_b200/csrc/tc_perm.cuh), compiled for the host with a CUDA-thread shim
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def perm_emu():
+    src = os.path.join(HERE, "emu", "perm_emu.cpp")
+    exe = os.path.join(BUILD, "perm_emu")
+    hdr = os.path.join(HERE, "..", "pyipn_b200", "csrc", "tc_perm.cuh")
+    os.makedirs(BUILD, exist_ok=True)
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-o", exe, src], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("T,seed,mean", [(0, 1, 0.9), (1, 2, 0.9), (31, 3, 0.9), (1024, 4, 0.9), (1025, 5, 2.0), (4100, 6, 0.8),
+                                          (3333, 7, 0.1), (2500, 8, 6.0)])
+def test_permutation_kernels_run_from_their_own_source(perm_emu, T, seed, mean):
+    """tc_perm_kernel (bins with counts first) and tc_perm_sorted_kernel (count classes 1, 2, 3, >= 4, 0 -- the product
+    epilogue's order): every CUDA thread an OS thread, real barriers and warp collectives; result = std::stable_sort, flags
+    (bins with counts, mode, sum n^2) exact, nothing written past the end.  Empty input, partial blocks, several blocks,
+    sparse and bright data."""
+    r = subprocess.run([perm_emu, str(T), str(seed), str(mean)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
