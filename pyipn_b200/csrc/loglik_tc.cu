@@ -33,62 +33,11 @@
 #include "loglik_common.cuh"
 #include "loglik_epilogue.cuh"
 #include "tc_perm.cuh"
+#include "tc_images.cuh"
 
 namespace ipn {
 
-namespace tc {
-constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
-#ifndef IPN_TC_TN
-#define IPN_TC_TN 32
-#endif
-constexpr int TN = IPN_TC_TN; // bins per tile (MMA N, TMEM columns per level)
-constexpr int NLEV = 4;       // level accumulators S2..S5
-constexpr int PW = 4;         // W digit planes
-constexpr int PP = 3;         // Phi digit planes
-#ifndef IPN_TC_EPI_WARPS
-#define IPN_TC_EPI_WARPS 16
-#endif
-#ifndef IPN_TC_GCOLS
-#define IPN_TC_GCOLS 16
-#endif
-constexpr int EPI_WARPS = IPN_TC_EPI_WARPS;  // 4 per TMEM lane quarter (and per SM sub-partition) rotating over column groups:
-                                             // 96 registers per thread, measured 3 % faster than 12 warps at 126
-constexpr int EPI_SLOTS = EPI_WARPS / 4;
-constexpr int GCOLS = IPN_TC_GCOLS;          // columns per epilogue work unit (batches of 8)
-constexpr int NH = GCOLS / 8;
-constexpr int GROUPS = TN / GCOLS; // work units per tile and lane quarter
-constexpr int EPI_ARRIVALS = 4 * GROUPS;  // one arrival per (lane quarter, group) and tile
-constexpr int NTHREADS = (3 + EPI_WARPS) * 32;
-// The warp scheduler favours the highest warp id among eligible warps: the two light but latency-critical roles
-// get the top ids so the epilogue warps sharing their sub-partitions cannot starve them.
-constexpr int PRODUCER_WARP = EPI_WARPS;      // 16
-constexpr int MMA_WARP = EPI_WARPS + 1;       // 17: issues the even tiles (accumulator buffer 0) and the TMEM copies of W
-constexpr int MMA_WARP2 = EPI_WARPS + 2;      // 18: issues the odd tiles (accumulator buffer 1) from another sub-partition
-constexpr int KPAD_MAX = 224;
-constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
-constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
-// A parity wait on an mbarrier is only sound if the waiter sees EVERY phase of that barrier (it cannot tell "two phases
-// away" from "done").  A warp of epilogue slot s owns the groups with (GROUPS tile + g) % EPI_SLOTS == s, so it skips tiles
-// (every other one with 4 slots and 2 groups, every third with 3 slots); with two MMA issuers tiles may also complete out
-// of order.  Hence every barrier an epilogue warp waits on is indexed by tile % (a multiple of the ownership period): all
-// uses of one barrier then belong to the same warps, and the others never look at it.  6 serves both 3 and 4 slots.
-constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks
-constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6
-constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
-constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after which the group -> slot assignment repeats
-static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
-constexpr int NBST = 128 / TN;             // depth of the Phi digit-plane ring (4 tiles of 32 bins: 86 KB)
-constexpr int NBUF = 256 / (NLEV * TN);    // accumulator buffers in TMEM columns [256, 512)
-static_assert(NBUF >= 2 && NBUF % 2 == 0 && NTF >= NBUF, "each accumulator buffer belongs to one issuer");
-constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
-}  // namespace tc
-
-struct TcDraw {
-    float ks;     // kappa = 2^-12 / sigma
-    float sigma;  // power of two
-    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64, 3 product (EPI_* below)
-    int pad;
-};
+// namespace tc (tile geometry), TcDraw, tc_draw_kernel / tc_wimg_kernel / tc_pimg_kernel: tc_images.cuh
 
 struct TcParams {
     const uint8_t* Wimg;  // [Sb][n_dt][a_bytes]
@@ -105,187 +54,6 @@ struct TcParams {
     int skip_math;            // experiment switch (IPN_TC_SKIP_MATH): epilogue only drains TMEM -> exposes the MMA-bound period
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
 };
-
-// ------------------------------------------------------------------------------------------------------
-// operand images (global memory, exactly the shared-memory byte order the UMMA descriptors expect:
-// K-major, no swizzle: [plane][k/16][row][k%16], i.e. 8x16-byte core matrices contiguous (SBO = 128 B),
-// next 16-byte K chunk after all rows (LBO = rows * 16 B))
-// ------------------------------------------------------------------------------------------------------
-// split_digits4: loglik_epilogue.cuh
-
-// sigma / kappa of every draw: sigma = largest power of two with sigma*max|W| <= 1 and sigma*|c| <= n_crows
-__global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const double* __restrict__ a,
-                               const double* __restrict__ b, const DrawConst* __restrict__ dc, const int* __restrict__ flags,
-                               TcDraw* __restrict__ td) {
-    const int sl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sl >= Sb) return;
-    const int64_t s = S0 + sl;
-    double mx = 0.0, sumw = 0.0;
-    for (int j = 0; j < J; ++j) {
-        const double aj = a[s * J + j], bj = b[s * J + j];
-        const double wj = kLog2e * sqrt(aj * aj + bj * bj);
-        mx = fmax(mx, wj);
-        sumw += wj;
-    }
-    const double c = fabs((double)dc[s].c_hi + (double)dc[s].c_lo);  // inf for amp == 0 (handled through the consts)
-    int e = 20;  // sigma = 2^e, start high and walk down
-    const double lim_c = (double)n_crows * (1.0 - 1e-6);
-    while (e > -6 && (ldexp(mx, e) > 1.0 || (isfinite(c) && ldexp(c, e) > lim_c))) --e;
-    TcDraw t;
-    t.sigma = (float)ldexp(1.0, e);
-    t.ks = (float)ldexp(1.0, -12 - e);
-    // fp32 epilogue error model: rms |dll| ~ 3.5e-8 ln2 y sqrt(sum n_i^2) with y ~ max(1, log2(A/B)) the size of
-    // log2(1+u).  Above ~2.5e-5 nats rms predicted (bright, coarsely binned data, or a source far above the background) the
-    // draw is evaluated with the compensated fp32 epilogue, above ~2.5e-4 with the fp64 one.  flags[1] = IPN_OPT_HIFI:
-    // 0 auto, 1 always fp64, 2 always plain fp32, 3 always compensated fp32.
-    const double sumsq = *reinterpret_cast<const double*>(flags + 2);
-    const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
-    // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
-    const double crit = ysc * ysc * sumsq;
-    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0))));
-    // flags[1] = 4 (opt-in, IPN_OPT_HIFI = 4): the product epilogue (EPI_PROD, loglik_epilogue.cuh) for the draws the plain
-    // fp32 epilogue would get, provided no exponent can leave [-120, 120] (|x| <= |c| + log2e sum_j |(a_j, b_j)|, the phases
-    // of all frequencies aligned; ~40 for a draw of the prior): that epilogue evaluates 2^x without clamps.  The other
-    // draws keep the automatic choice.
-    if (flags[1] == 4 && t.hifi == 0 && (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0) t.hifi = 3;
-    t.pad = 0;
-    td[sl] = t;
-}
-
-// W digit planes of one (draw, tile of 128 delays).  One thread = one (delay row, 16-wide K chunk).
-__global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpad, const double* __restrict__ omega,
-                                                      const double* __restrict__ a, const double* __restrict__ b,
-                                                      const DrawConst* __restrict__ dc, const TcDraw* __restrict__ td,
-                                                      int64_t G, const double* __restrict__ delays, int n_dt,
-                                                      uint32_t a_bytes, uint32_t a_plane, uint8_t* __restrict__ Wimg) {
-    const int row = threadIdx.x;  // 0..127
-    const int kc = blockIdx.x;    // K chunk of 16
-    const int dt = blockIdx.y;
-    const int sl = blockIdx.z;
-    const int64_t s = S0 + sl;
-    const int64_t g = (int64_t)dt * tc::TM + row;
-    const double sigma = (double)td[sl].sigma;
-    const double cs = (double)dc[s].c_hi + (double)dc[s].c_lo;
-    const int ncrow = Kpad - 2 * J;
-    alignas(16) int8_t d[4][16];
-    const double dl = (g < G) ? delays[g] : 0.0;
-    for (int kk = 0; kk < 16; kk += 2) {
-        const int k = kc * 16 + kk;
-        int q0 = 0, q1 = 0;
-        if (g < G) {
-            if (k < 2 * J) {
-                const int j = k >> 1;
-                const double w = omega[s * J + j], aj = a[s * J + j], bj = b[s * J + j];
-                double sn, cn;
-                sincos(w * dl, &sn, &cn);
-                // saturate instead of wrapping if a caller of the _dev entry point passes amplitudes beyond the supported range
-                q0 = (int)llrint(fmin(fmax(kLog2e * (aj * cn - bj * sn) * sigma, -1.0), 1.0) * 1073741824.0);
-                q1 = (int)llrint(fmin(fmax(kLog2e * (aj * sn + bj * cn) * sigma, -1.0), 1.0) * 1073741824.0);
-            } else if (isfinite(cs)) {
-                // additive constant c spread exactly over the ncrow constant rows
-                const long long tot = llrint(cs * sigma * 1073741824.0);
-                const long long base = tot / ncrow, rem = tot - base * ncrow;  // |rem| < ncrow, same sign as tot
-                const int i0 = k - 2 * J, i1 = i0 + 1;
-                const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
-                q0 = (int)(base + (i0 < ar ? sg : 0));
-                q1 = (int)(base + (i1 < ar ? sg : 0));
-            }
-        }
-        split_digits4(q0, d[0][kk], d[1][kk], d[2][kk], d[3][kk]);
-        split_digits4(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[3][kk + 1]);
-    }
-    uint8_t* img = Wimg + ((int64_t)sl * n_dt + dt) * a_bytes;
-#pragma unroll
-    for (int pl = 0; pl < 4; ++pl)
-        *reinterpret_cast<int4*>(img + (size_t)pl * a_plane + ((size_t)kc * tc::TM + row) * 16) =
-            *reinterpret_cast<const int4*>(d[pl]);
-}
-
-// tc_perm_count_kernel / tc_perm_kernel / tc_perm_sorted_count_kernel / tc_perm_sorted_kernel: tc_perm.cuh
-
-// Phi digit planes + Poisson constants of one (draw, tile of 64 permuted bins).
-// 256 threads: row = tid % 32, eight threads per row interleave the 16-wide K chunks.
-__global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
-                                                      const double* __restrict__ exposure, const int64_t* __restrict__ counts,
-                                                      const int* __restrict__ perm, const int* __restrict__ n_nz,
-                                                      const double* __restrict__ omega, const DrawConst* __restrict__ dc,
-                                                      const TcDraw* __restrict__ td, int n_bt, uint32_t b_bytes, uint32_t b_plane,
-                                                      uint8_t* __restrict__ Pimg) {
-    const int row = threadIdx.x & (tc::TN - 1);
-    const int kg = threadIdx.x / tc::TN;
-    const int bt = blockIdx.x;
-    const int sl = blockIdx.y;
-    const int64_t s = S0 + sl;
-    const int64_t pos = (int64_t)bt * tc::TN + row;
-    const bool valid = pos < T;
-    const int64_t i = valid ? perm[pos] : 0;
-    const double t = valid ? time[i] : 0.0;
-    const float th = (float)t, tl = (float)(t - (double)(float)t);
-    uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
-    // omega / 2 pi of this draw as fp32 hi + lo: the phases are formed without fp64 arithmetic (sincos_phase_df)
-    __shared__ float2 s_w[IPN_MAX_J];
-    for (int j = threadIdx.x; j < J; j += 256) {
-        const double wt = omega[s * J + j] * 0.15915494309189534561;
-        const float wh = (float)wt;
-        s_w[j] = make_float2(wh, (float)(wt - (double)wh));
-    }
-    __syncthreads();
-    for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
-        alignas(16) int8_t d[3][16];
-#pragma unroll
-        for (int kk = 0; kk < 16; kk += 2) {
-            const int k = kc * 16 + kk;
-            int q0 = 0, q1 = 0;
-            if (valid) {
-                if (k < 2 * J) {
-                    float sn, cn;
-                    const float2 w = s_w[k >> 1];
-                    if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
-                    q0 = __float2int_rn(cn * 4194304.0f);  // cos row
-                    q1 = __float2int_rn(sn * 4194304.0f);  // sin row
-                } else {
-                    q0 = q1 = 4194304;  // constant rows: Phi = 1
-                }
-            }
-            int8_t dummy;
-            split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
-            split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
-        }
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
-            *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
-                *reinterpret_cast<const int4*>(d[pl]);
-    }
-    if (kg == 0) {
-        const DrawConst dcs = dc[s];
-        const bool src = isfinite(dcs.c_hi);  // amp == 0: the likelihood is the constant C_s, every term is zero
-        const double kap = (valid && src) ? exposure[i] * dcs.kap : 0.0;
-        const float khi = (float)kap;
-        float4 c;
-        c.x = (valid && src) ? (float)counts[i] : 0.0f;
-        c.y = khi;
-        c.z = (float)(kap - (double)khi);
-        c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
-        float n_uniform = 0.0f;
-        if (td[sl].hifi == 3) {
-            // product epilogue: n as an integer, and in the tile's flag block the count value all its bins share (1, 2 or 3;
-            // 0 = mixed, four or more, or padding: the epilogue then loops per bin).  The threads here are rows 0 .. TN - 1.
-            const int n_int = (valid && src) ? (int)min(counts[i], (int64_t)0x7fffffff) : 0;
-            c.w = __int_as_float(n_int);
-            const unsigned act = __activemask();
-            const int n0 = __shfl_sync(act, n_int, 0);
-            if (__all_sync(act, n_int == n0) && n0 >= 1 && n0 <= 3) n_uniform = (float)n0;
-        }
-        *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
-        if (row == 0) {
-            float4 f;
-            f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
-            f.y = n_uniform;
-            f.z = f.w = 0.0f;
-            *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)tc::TN * 16) = f;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers

@@ -16,82 +16,7 @@
 #include <thread>
 #include <vector>
 
-#define IPN_HOST_EMU 1
-#define __global__
-#define __device__
-#define __forceinline__ inline
-#define __shared__ static  // one block runs at a time: a function-local static IS the block's shared memory
-#define __launch_bounds__(...)
-
-struct Dim3 {
-    unsigned x = 1, y = 1, z = 1;
-};
-static thread_local Dim3 threadIdx, blockIdx;
-static Dim3 blockDim, gridDim;
-
-namespace shim {
-struct Warp {
-    std::barrier<> bar{32};
-    uint64_t slot[32];
-};
-static std::unique_ptr<std::barrier<>> block_bar;
-static std::vector<std::unique_ptr<Warp>> warps;
-static thread_local Warp* my_warp;
-static thread_local int lane;
-
-template <class T>
-inline T exchange(T v, int src_lane) {
-    static_assert(sizeof(T) <= 8, "");
-    uint64_t raw = 0;
-    std::memcpy(&raw, &v, sizeof(T));
-    my_warp->slot[lane] = raw;
-    my_warp->bar.arrive_and_wait();
-    const uint64_t got = my_warp->slot[src_lane];
-    my_warp->bar.arrive_and_wait();  // nobody overwrites a slot before everyone has read
-    T r;
-    std::memcpy(&r, &got, sizeof(T));
-    return r;
-}
-
-template <class Kernel, class... Args>
-void launch(Kernel k, unsigned grid, unsigned block, Args... args) {
-    gridDim.x = grid;
-    blockDim.x = block;
-    for (unsigned b = 0; b < grid; ++b) {
-        block_bar = std::make_unique<std::barrier<>>(block);
-        warps.clear();
-        for (unsigned w = 0; w < block / 32; ++w) warps.push_back(std::make_unique<Warp>());
-        std::vector<std::thread> th;
-        th.reserve(block);
-        for (unsigned t = 0; t < block; ++t)
-            th.emplace_back([=] {
-                threadIdx.x = t;
-                blockIdx.x = b;
-                my_warp = warps[t / 32].get();
-                lane = (int)(t % 32);
-                k(args...);
-            });
-        for (auto& x : th) x.join();
-    }
-}
-}  // namespace shim
-
-inline void __syncthreads() { shim::block_bar->arrive_and_wait(); }
-template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int o) { return shim::exchange(v, shim::lane ^ o); }
-template <class T>
-inline T __shfl_up_sync(unsigned, T v, int o) { return shim::exchange(v, shim::lane >= o ? shim::lane - o : shim::lane); }
-template <class T>
-inline T __shfl_sync(unsigned, T v, int src) { return shim::exchange(v, src); }
-inline unsigned __ballot_sync(unsigned, bool p) {
-    unsigned m = 0;
-    shim::my_warp->slot[shim::lane] = p ? 1u : 0u;
-    shim::my_warp->bar.arrive_and_wait();
-    for (int l = 0; l < 32; ++l) m |= (unsigned)shim::my_warp->slot[l] << l;
-    shim::my_warp->bar.arrive_and_wait();
-    return m;
-}
-inline int __popc(unsigned x) { return __builtin_popcount(x); }
+#include "cuda_shim.h"
 
 #include "../../pyipn_b200/csrc/tc_perm.cuh"
 
@@ -149,9 +74,7 @@ int main(int argc, char** argv) {
     // the count-sorted permutation of the product epilogue: classes 1, 2, 3, >= 4, then 0, each in its original order
     std::fill(perm.begin(), perm.end(), -1);
     std::fill(blk_cnt.begin(), blk_cnt.end(), -7);
-    std::stable_sort(want.begin(), want.end(), [&](int a, int b) { return cls_of(counts[a]) < cls_of(counts[b]); });
-    // (want was already a stable partition; re-sorting from identity keeps the reference independent of it)
-    for (int64_t i = 0; i < T; ++i) want[i] = (int)i;
+    for (int64_t i = 0; i < T; ++i) want[i] = (int)i;  // from the identity again: independent of the partition above
     std::stable_sort(want.begin(), want.end(), [&](int a, int b) { return cls_of(counts[a]) < cls_of(counts[b]); });
     if (n_blk > 0) shim::launch(ipn::tc_perm_sorted_count_kernel, n_blk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
     shim::launch(ipn::tc_perm_sorted_kernel, n_blk > 0 ? n_blk : 1, 1024, T, counts.data(), n_blk, blk_cnt.data(), blk_sq.data(),

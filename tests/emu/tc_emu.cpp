@@ -15,6 +15,7 @@
 //   tc_emu funcs                          -> JSON with error statistics of exp2_poly / exp2_hilo / sincos_* / poisson_term
 //   tc_emu grid <in.bin> <bias> <noise>   -> for every delay: ll by the fp32, compensated fp32 and fp64 epilogues
 //   tc_emu gridprod <in.bin>              -> for every delay: ll by the product epilogue (count-sorted bins, IPN_OPT_HIFI = 4)
+//   tc_emu images <in.bin> <0 | 4> <out>   -> the restated operand images in the device's byte order (cf. images_emu.cpp)
 //   tc_emu rff <in.bin> <out.bin>         -> rff_eval_kernel's arithmetic (rff_terms.cuh): lambda (S, T) float64 + the tier of every draw
 #include <cmath>
 #include <cstdint>
@@ -148,7 +149,7 @@ static bool rd(FILE* f, T* p, size_t n) {
     return std::fread(p, sizeof(T), n, f) == n;
 }
 
-static int run_grid(const char* path, double bias, double noise, bool prod) {
+static int run_grid(const char* path, double bias, double noise, bool prod, const char* dump_path = nullptr) {
     g_lg2_bias = bias;
     g_lg2_noise = noise;
     FILE* f = std::fopen(path, "rb");
@@ -273,12 +274,12 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
         cc.y = khi;
         cc.z = (float)(kap - (double)khi);
         cc.w = cc.x * 1.44269504f;
-        if (prod) cc.w = __int_as_float((valid && src) ? (int)std::min<int64_t>(counts[i], 0x7fffffff) : 0);
+        if (prod && prod_mode == 3) cc.w = __int_as_float((valid && src) ? (int)std::min<int64_t>(counts[i], 0x7fffffff) : 0);
         cst[pos] = cc;
     }
     // tile flag block of the product epilogue: the count value all 32 bins share (1, 2, 3), else 0
     std::vector<int> n_uniform(n_bt, 0);
-    if (prod)
+    if (prod && prod_mode == 3)
         for (int bt = 0; bt < n_bt; ++bt) {
             const int n0 = __float_as_int(cst[(size_t)bt * cfg::TN].w);
             bool all = n0 >= 1 && n0 <= 3;
@@ -291,31 +292,74 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
     const double ksd = (double)ks, sigma = (double)sigma_f;
     const double cs = (double)dc.c_hi + (double)dc.c_lo;
 
-    std::printf("{\"auto_mode\": %d, \"prod_mode\": %d, \"xmax\": %.6g, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
-                auto_mode, prod_mode, xmax, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
-    std::vector<int8_t> W((size_t)4 * Kpad);
-    std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
-    for (int64_t g = 0; g < G; ++g) {
-        // tc_wimg_kernel: W digit planes of this delay
-        const double dl = delays[g];
+    // tc_wimg_kernel: W digit planes of one delay (rows beyond G are zero)
+    auto w_digits = [&](int64_t g, std::vector<int8_t>& W) {
+        const double dl = g < G ? delays[g] : 0.0;
         for (int k = 0; k < Kpad; k += 2) {
             int q0 = 0, q1 = 0;
-            if (k < 2 * J) {
-                const int j = k >> 1;
-                const double sn = std::sin(omega[j] * dl), cn = std::cos(omega[j] * dl);
-                q0 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * cn - b[j] * sn) * sigma, -1.0), 1.0) * 1073741824.0);
-                q1 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * sn + b[j] * cn) * sigma, -1.0), 1.0) * 1073741824.0);
-            } else if (std::isfinite(cs)) {
-                const long long tot = std::llrint(cs * sigma * 1073741824.0);
-                const long long base = tot / ncrow, rem = tot - base * ncrow;
-                const int i0 = k - 2 * (int)J, i1 = i0 + 1;
-                const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
-                q0 = (int)(base + (i0 < ar ? sg : 0));
-                q1 = (int)(base + (i1 < ar ? sg : 0));
+            if (g < G) {
+                if (k < 2 * J) {
+                    const int j = k >> 1;
+                    const double sn = std::sin(omega[j] * dl), cn = std::cos(omega[j] * dl);
+                    q0 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * cn - b[j] * sn) * sigma, -1.0), 1.0) * 1073741824.0);
+                    q1 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * sn + b[j] * cn) * sigma, -1.0), 1.0) * 1073741824.0);
+                } else if (std::isfinite(cs)) {
+                    const long long tot = std::llrint(cs * sigma * 1073741824.0);
+                    const long long base = tot / ncrow, rem = tot - base * ncrow;
+                    const int i0 = k - 2 * (int)J, i1 = i0 + 1;
+                    const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
+                    q0 = (int)(base + (i0 < ar ? sg : 0));
+                    q1 = (int)(base + (i1 < ar ? sg : 0));
+                }
             }
             split_digits4(q0, W[0 * Kpad + k], W[1 * Kpad + k], W[2 * Kpad + k], W[3 * Kpad + k]);
             split_digits4(q1, W[0 * Kpad + k + 1], W[1 * Kpad + k + 1], W[2 * Kpad + k + 1], W[3 * Kpad + k + 1]);
         }
+    };
+    std::vector<int8_t> W((size_t)4 * Kpad);
+
+    if (dump_path) {
+        // the images in the device's byte order ([plane][k / 16][row][k % 16], constants and flag block behind the Phi planes),
+        // to be compared with what the kernels themselves produce (tests/emu/images_emu.cpp)
+        const int TM = 128, n_dt = (int)((G + TM - 1) / TM);
+        const size_t a_plane = (size_t)Kpad * TM, b_plane = (size_t)Kpad * cfg::TN;
+        const size_t a_bytes = 4 * a_plane, b_bytes = 3 * b_plane + cfg::TN * 16 + 16;
+        std::vector<uint8_t> Wi((size_t)n_dt * a_bytes, 0), Pi((size_t)n_bt * b_bytes, 0);
+        for (int64_t g = 0; g < (int64_t)n_dt * TM; ++g) {
+            w_digits(g, W);
+            for (int pl = 0; pl < 4; ++pl)
+                for (int k = 0; k < Kpad; ++k)
+                    Wi[(size_t)(g / TM) * a_bytes + pl * a_plane + ((size_t)(k / 16) * TM + g % TM) * 16 + k % 16] = (uint8_t)W[pl * Kpad + k];
+        }
+        for (int64_t pos = 0; pos < Tpad; ++pos) {
+            uint8_t* img = &Pi[(size_t)(pos / cfg::TN) * b_bytes];
+            const int row = (int)(pos % cfg::TN);
+            for (int pl = 0; pl < 3; ++pl)
+                for (int k = 0; k < Kpad; ++k)
+                    img[pl * b_plane + ((size_t)(k / 16) * cfg::TN + row) * 16 + k % 16] = (uint8_t)P[((size_t)pl * Tpad + pos) * Kpad + k];
+            std::memcpy(img + 3 * b_plane + (size_t)row * 16, &cst[pos], 16);
+            if (row == 0) {
+                const float4 fl = {(pos < n_nz) ? 1.0f : 0.0f, (float)n_uniform[pos / cfg::TN], 0.0f, 0.0f};
+                std::memcpy(img + 3 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
+            }
+        }
+        FILE* g = std::fopen(dump_path, "wb");
+        if (!g) return 2;
+        const int ih[4] = {Kpad, n_dt, n_bt, prod ? prod_mode : auto_mode};
+        const float fh[2] = {ks, sigma_f};
+        std::fwrite(ih, 4, 4, g);
+        std::fwrite(fh, 4, 2, g);
+        std::fwrite(Wi.data(), 1, Wi.size(), g);
+        std::fwrite(Pi.data(), 1, Pi.size(), g);
+        std::fclose(g);
+        return 0;
+    }
+
+    std::printf("{\"auto_mode\": %d, \"prod_mode\": %d, \"xmax\": %.6g, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
+                auto_mode, prod_mode, xmax, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
+    std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
+    for (int64_t g = 0; g < G; ++g) {
+        w_digits(g, W);
         double R[4] = {0.0, 0.0, 0.0, 0.0};  // per epilogue mode (fp32, compensated, fp64, product), the float64 atomicAdd target
         for (int chunk = 0; chunk < nchunk; ++chunk) {
             const int bt0 = chunk * tiles_per_chunk, bt1 = std::min(n_bt, bt0 + tiles_per_chunk);
@@ -359,7 +403,7 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
                             t5[j] = S5[o + j];
                         }
                         const float4* cp = &cst[(size_t)bt * cfg::TN + o];
-                        if (prod) {
+                        if (prod && prod_mode == 3) {
 #define EMU_PROD_UNITS(NU) epi_units8_prod<NU>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[2][slot], scomp[2][slot], pP[slot], pE[slot])
                             if (!has_counts) EMU_PROD_UNITS(0);
                             else if (n_uniform[bt] == 1) EMU_PROD_UNITS(1);
@@ -388,7 +432,8 @@ static int run_grid(const char* path, double bias, double noise, bool prod) {
         }
         // finalize_kernel
         std::printf("[");
-        for (int m = prod ? 3 : 0; m < (prod ? 4 : 3); ++m) {
+        // gridprod: what IPN_OPT_HIFI = 4 returns -- the product epilogue if the draw qualifies, else the automatic choice
+        for (int m = prod ? prod_mode : 0; m < (prod ? prod_mode + 1 : 3); ++m) {
             const double v = dc.C + kLn2 * R[m];
             if (std::isfinite(v))
                 std::printf("%.17g%s", v, (m < 2 && !prod) ? ", " : "");
@@ -466,6 +511,7 @@ int main(int argc, char** argv) {
     if (argc >= 2 && !std::strcmp(argv[1], "funcs")) return run_funcs();
     if (argc >= 5 && !std::strcmp(argv[1], "grid")) return run_grid(argv[2], std::atof(argv[3]), std::atof(argv[4]), false);
     if (argc >= 3 && !std::strcmp(argv[1], "gridprod")) return run_grid(argv[2], 0.0, 0.0, true);
+    if (argc >= 5 && !std::strcmp(argv[1], "images")) return run_grid(argv[2], 0.0, 0.0, std::atoi(argv[3]) == 4, argv[4]);
     if (argc >= 4 && !std::strcmp(argv[1], "rff")) return run_rff(argv[2], argv[3]);
     std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise> | tc_emu gridprod <in.bin> | tc_emu rff <in.bin> <out.bin>\n");
     return 64;

@@ -331,3 +331,44 @@ def test_permutation_kernels_run_from_their_own_source(perm_emu, T, seed, mean):
     sparse and bright data."""
     r = subprocess.run([perm_emu, str(T), str(seed), str(mean)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the operand-image kernels themselves (tc_images.cuh + tc_perm.cuh) on the host, against the restatement used above
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def images_emu():
+    src = os.path.join(HERE, "emu", "images_emu.cpp")
+    exe = os.path.join(BUILD, "images_emu")
+    deps = [src, os.path.join(HERE, "emu", "cuda_shim.h")] + [os.path.join(HERE, "..", "pyipn_b200", "csrc", h) for h in
+                                                              ("tc_images.cuh", "tc_perm.cuh", "loglik_epilogue.cuh", "loglik_common.cuh")]
+    os.makedirs(BUILD, exist_ok=True)
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(p) for p in deps):
+        subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-o", exe, src], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("T,G,kw", [(1000 + 17, 130, {}), (333, 5, dict(bkg=15000.0, boost=12000.0)), (64, 1, {}),
+                                     (700, 129, dict(bkg=1.0e6, boost=1.0e6))])
+def test_restated_images_equal_the_kernels_own(emu, images_emu, tmp_path, T, G, kw):
+    """tc_perm*_kernel, tc_draw_kernel, tc_wimg_kernel and tc_pimg_kernel run on the host from their own source (every CUDA
+    thread an OS thread): scale, epilogue choice, W image, Phi image, per-bin constants and tile flags are byte for byte what
+    the restatement inside tc_emu builds -- for the default partition and for the product epilogue's count-sorted order
+    (integer counts and the per-tile count flag).  So the full-size emulation above runs on the images the device builds."""
+    w = synth.delay_grid_workload(T=T, G=G, S=1, **kw)
+    path = os.path.join(str(tmp_path), "in.bin")
+    with open(path, "wb") as f:
+        np.array([T, w["omega"].shape[1], G], dtype=np.int64).tofile(f)
+        np.array([float(w["amp"][0]), float(w["bkg"][0])], dtype=np.float64).tofile(f)
+        for arr, dt in ((w["time"], np.float64), (w["exposure"], np.float64), (w["counts"], np.int64), (w["omega"][0], np.float64),
+                        (w["a"][0], np.float64), (w["b"][0], np.float64), (w["delays"], np.float64)):
+            np.ascontiguousarray(arr, dtype=dt).tofile(f)
+    modes = set()
+    for mode in (0, 4):
+        a, b = os.path.join(str(tmp_path), "restated.bin"), os.path.join(str(tmp_path), "kernels.bin")
+        subprocess.run([emu, "images", path, str(mode), a], check=True)
+        subprocess.run([images_emu, path, str(mode), b], check=True, timeout=600)
+        A, B = np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)
+        assert A.size == B.size and np.array_equal(A, B), (mode, A.size, B.size, np.nonzero(A != B)[0][:8] if A.size == B.size else None)
+        modes.add(int(B[:16].view(np.int32)[3]))
+    assert modes <= {0, 1, 2, 3} and (3 in modes) == (0 in modes)  # mode 4 turns exactly the plain-fp32 draws into product draws
