@@ -44,10 +44,11 @@ constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n 
 // (every other one with 4 slots and 2 groups, every third with 3 slots); with two MMA issuers tiles may also complete out
 // of order.  Hence every barrier an epilogue warp waits on is indexed by tile % (a multiple of the ownership period): all
 // uses of one barrier then belong to the same warps, and the others never look at it.  6 serves both 3 and 4 slots.
-constexpr int NCST = 6;                    // depth of the shared-memory ring of those constant blocks
-constexpr int NTF = 6;                     // "accumulators complete" barriers: tile % 6
+// (five slots -- 20 epilogue warps, an untried experiment -- need a multiple of 5: 10)
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after which the group -> slot assignment repeats
+constexpr int NCST = (6 % OWN_PERIOD == 0) ? 6 : 2 * OWN_PERIOD;  // depth of the shared-memory ring of those constant blocks
+constexpr int NTF = NCST;                  // "accumulators complete" barriers: tile % NTF
 static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
 constexpr int NBST = 128 / TN;             // depth of the Phi digit-plane ring (4 tiles of 32 bins: 86 KB)
 constexpr int NBUF = 256 / (NLEV * TN);    // accumulator buffers in TMEM columns [256, 512)
