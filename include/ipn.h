@@ -53,8 +53,12 @@ typedef struct ipn_ctx ipn_ctx;
 /* ---- context -------------------------------------------------------------------------------------- */
 int ipn_ctx_create(int device, ipn_ctx** out);
 void ipn_ctx_destroy(ipn_ctx* ctx);
-/* borrow an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+/* borrow an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).  The handle is taken
+ * literally: NULL is CUDA's legacy default stream (torch's current stream outside a torch.cuda.stream(...) block).
+ * A new context runs on a stream of its own (a blocking stream: implicitly ordered with the legacy default stream);
+ * ipn_ctx_use_own_stream returns to it. */
 int ipn_ctx_set_stream(ipn_ctx* ctx, void* cuda_stream);
+int ipn_ctx_use_own_stream(ipn_ctx* ctx);
 int ipn_ctx_synchronize(ipn_ctx* ctx);
 int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value);
 /* number of kernels of THIS library launched through the context so far (bench.py's gpu_launches)     */
@@ -65,6 +69,9 @@ double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx);
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches);
 /* which contraction back-end the most recent log-likelihood call used: 1 = FP32 pipe, 2 = tcgen05 (0 = none yet) */
 int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx);
+/* draws per internal batch of the most recent log-likelihood call (the operand-image scratch is bounded, so a call with many
+ * draws is processed in batches; bench.py spreads its oracle spot check over every batch) */
+int64_t ipn_ctx_last_draw_batch(const ipn_ctx* ctx);
 const char* ipn_last_error(void);
 const char* ipn_version(void);
 
@@ -158,7 +165,8 @@ int ipn_sky_credible_dev(ipn_ctx* ctx, int64_t P, int64_t S, const double* d_ll,
                          double* d_prob, double* d_level, int64_t* d_order, double* d_log_norm);
 
 /* ---- device micro-benchmarks used by bench.py for the roofline denominators ------------------------
- * which: 0 = FP32 FMA loop (returns TFLOP/s), 1 = MUFU.EX2 loop (returns Tops/s). */
+ * which: 0 = FP32 FMA loop (returns TFLOP/s), 1 = MUFU.EX2 loop (returns Tops/s), 2 = tcgen05.mma kind::i8 issue loop
+ * (M = 128, N = 32, K = 32, A from tensor memory -- the hot kernel's MMA shape; returns int8 TOP/s, 2 ops per MAC). */
 int ipn_microbench(ipn_ctx* ctx, int which, double* result);
 
 #ifdef __cplusplus

@@ -15,9 +15,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libipn_b200.so")
+# the same library with the experiment / test hooks of the hot kernel compiled in (-DIPN_TC_HOOKS: environment switches that
+# re-pace the pipeline or skip work); only tests/ and tools/ load it, the shipped library has none of it
+HOOKS_LIB = os.path.join(HERE, "libipn_b200_hooks.so")
+HOOKS_SOURCES = ["loglik_tc.cu", "rff_eval.cu"]  # the translation units that contain hooks
 OBJDIR = os.path.join(CSRC, "build")
 
-SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu", "correlate.cu", "binning.cu", "thinning.cu", "sky_post.cu"]
+SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu", "correlate.cu", "binning.cu", "thinning.cu", "sky_post.cu", "umma_peak.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,34 +56,38 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     stamp_file = os.path.join(OBJDIR, "stamp")
     stamp = _stamp(sources)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+    if (not force and os.path.exists(LIB) and os.path.exists(HOOKS_LIB) and os.path.exists(stamp_file)
+            and open(stamp_file).read() == stamp):
         return LIB
     nvcc = _nvcc()
     log_path = os.path.join(OBJDIR, "ptxas.log")
 
-    def compile_one(src):
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job):
+        src, hooks = job
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".hooks.o" if hooks else ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DIPN_TC_HOOKS"] if hooks else []), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        return src, obj, r
+        return src, hooks, obj, r
 
-    objs, logs = [], []
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
-        for src, obj, r in ex.map(compile_one, sources):
-            logs.append(f"==== {src} ====\n{r.stdout}\n{r.stderr}")
+    jobs = [(s, False) for s in sources] + [(s, True) for s in sources if s in HOOKS_SOURCES]
+    objs, hook_objs, logs = {}, {}, []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        for src, hooks, obj, r in ex.map(compile_one, jobs):
+            logs.append(f"==== {src}{' (-DIPN_TC_HOOKS)' if hooks else ''} ====\n{r.stdout}\n{r.stderr}")
             if r.returncode != 0:
                 sys.stderr.write(logs[-1])
                 raise RuntimeError(f"nvcc failed on {src}")
-            objs.append(obj)
+            (hook_objs if hooks else objs)[src] = obj
     with open(log_path, "w") as f:
         f.write("\n".join(logs))
     if verbose:
         sys.stderr.write("\n".join(logs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc link failed")
+    for lib, sel in ((LIB, objs), (HOOKS_LIB, {**objs, **hook_objs})):
+        cmd = [nvcc, "-shared", "-o", lib, *[sel[s] for s in sources], "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc link failed")
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB

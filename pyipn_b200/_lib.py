@@ -13,6 +13,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IPN_B200_LIB") or os.path.join(HERE, "libipn_b200.so")  # IPN_B200_LIB: explicit path to the library
+# the same library built with -DIPN_TC_HOOKS (pacing / work-skipping switches of the hot kernel); tests/ and tools/ only
+HOOKS_LIB_PATH = os.path.join(HERE, "libipn_b200_hooks.so")
 
 IPN_OK = 0
 IPN_ERR_INVALID_ARGUMENT = -1
@@ -28,8 +30,8 @@ OPT_HIFI = 4
 
 # every symbol include/ipn.h declares (tests/test_abi.py checks the list against the header and the .so)
 EXPORTS = (
-    "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
-    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_last_error", "ipn_version",
+    "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_use_own_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
+    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_ctx_last_draw_batch", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
     "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench", "ipn_sky_credible", "ipn_sky_credible_dev",
 )
@@ -41,32 +43,33 @@ class IpnError(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 _lib_lock = threading.Lock()
 
 _p = C.c_void_p
 _i64 = C.c_int64
 
 
-def load_library():
-    """Load (once) and return the ctypes handle; raises IpnError if the CUDA library has not been built."""
-    global _lib
+def load_library(path: str | None = None):
+    """Load (once per path) and return the ctypes handle; raises IpnError if the CUDA library has not been built."""
+    path = path or LIB_PATH
     with _lib_lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
+        if path in _libs:
+            return _libs[path]
+        if not os.path.exists(path):
             raise IpnError(
                 IPN_ERR_NO_DEVICE,
-                f"{LIB_PATH} not found: build it with `python -m pyipn_b200._build` "
+                f"{path} not found: build it with `python -m pyipn_b200._build` "
                 "(pyipn_b200 has no CPU fallback and will not compute without its CUDA library)",
             )
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         lib.ipn_last_error.restype = C.c_char_p
         lib.ipn_version.restype = C.c_char_p
         lib.ipn_ctx_create.argtypes = [C.c_int, C.POINTER(_p)]
         lib.ipn_ctx_destroy.argtypes = [_p]
         lib.ipn_ctx_destroy.restype = None
         lib.ipn_ctx_set_stream.argtypes = [_p, _p]
+        lib.ipn_ctx_use_own_stream.argtypes = [_p]
         lib.ipn_ctx_synchronize.argtypes = [_p]
         lib.ipn_ctx_set_option.argtypes = [_p, C.c_int, _i64]
         lib.ipn_ctx_launch_count.argtypes = [_p]
@@ -74,6 +77,8 @@ def load_library():
         lib.ipn_ctx_last_kernel_ms.argtypes = [_p]
         lib.ipn_ctx_last_kernel_ms.restype = C.c_double
         lib.ipn_ctx_last_loglik_impl.argtypes = [_p]
+        lib.ipn_ctx_last_draw_batch.argtypes = [_p]
+        lib.ipn_ctx_last_draw_batch.restype = _i64
         lib.ipn_ctx_last_main_kernel_ms.argtypes = [_p, C.POINTER(_i64)]
         lib.ipn_ctx_last_main_kernel_ms.restype = C.c_double
         rff_args = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]
@@ -96,7 +101,7 @@ def load_library():
         sky_args = [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]
         lib.ipn_sky_credible.argtypes = sky_args
         lib.ipn_sky_credible_dev.argtypes = sky_args
-        _lib = lib
+        _libs[path] = lib
         return lib
 
 
@@ -119,8 +124,8 @@ def _ptr(arr):
 class Context:
     """One libipn_b200 context = one GPU.  Host-array methods take/return numpy; ``*_dev`` take raw device pointers."""
 
-    def __init__(self, device: int = 0):
-        self._lib = load_library()
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self._lib = load_library(lib_path)
         h = _p()
         _check(self._lib, self._lib.ipn_ctx_create(int(device), C.byref(h)))
         self._h = h
@@ -145,7 +150,12 @@ class Context:
 
     # ---- plumbing ------------------------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None):
-        _check(self._lib, self._lib.ipn_ctx_set_stream(self._h, _p(cuda_stream or 0)))
+        """Run on ``cuda_stream`` (a raw ``cudaStream_t`` handle such as ``torch.cuda.current_stream().cuda_stream``; 0 is
+        CUDA's legacy default stream, taken literally); ``None`` returns to the context's own stream."""
+        if cuda_stream is None:
+            _check(self._lib, self._lib.ipn_ctx_use_own_stream(self._h))
+        else:
+            _check(self._lib, self._lib.ipn_ctx_set_stream(self._h, _p(int(cuda_stream))))
 
     def synchronize(self):
         _check(self._lib, self._lib.ipn_ctx_synchronize(self._h))
@@ -171,6 +181,10 @@ class Context:
     @property
     def last_loglik_impl(self) -> int:
         return int(self._lib.ipn_ctx_last_loglik_impl(self._h))
+
+    @property
+    def last_draw_batch(self) -> int:
+        return int(self._lib.ipn_ctx_last_draw_batch(self._h))
 
     def microbench(self, which: int) -> float:
         out = C.c_double(0.0)

@@ -173,7 +173,9 @@ int ipn_ctx_create(int device, ipn_ctx** out) {
     ipn_ctx* ctx = new ipn_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // a BLOCKING stream: it keeps the implicit ordering with the legacy default stream (handle 0), so work a caller
+    // enqueues there before / after a _dev call is ordered with the library's kernels without further ado
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamDefault) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -208,7 +210,16 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
 int ipn_ctx_set_stream(ipn_ctx* ctx, void* cuda_stream) {
     int rc = ctx_guard(ctx);
     if (rc) return rc;
-    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    // the handle is taken literally: NULL is CUDA's legacy default stream (what torch.cuda.current_stream().cuda_stream
+    // is unless the caller entered a torch.cuda.stream(...) block), exactly as in every CUDA runtime call
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return IPN_OK;
+}
+
+int ipn_ctx_use_own_stream(ipn_ctx* ctx) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    ctx->stream = ctx->own_stream;
     return IPN_OK;
 }
 
@@ -251,6 +262,7 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
 uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx) { return ctx ? ctx->last_impl : 0; }
+int64_t ipn_ctx_last_draw_batch(const ipn_ctx* ctx) { return ctx ? ctx->last_draw_batch : 0; }
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches) {
     if (!ctx) return 0.0;
     if (launches) *launches = ctx->last_main_launches;

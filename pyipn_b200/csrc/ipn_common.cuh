@@ -56,6 +56,7 @@ struct ipn_ctx {
     double last_main_ms = 0.0;
     int64_t last_main_launches = 0;
     int last_impl = 0;
+    int64_t last_draw_batch = 0;
     // options
     int loglik_impl = 0;
     int precise_w = 1;

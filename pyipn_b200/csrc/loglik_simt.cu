@@ -253,6 +253,7 @@ int run_loglik_grid_simt(ipn_ctx* ctx, int64_t T, const double* time, const doub
     if (Sbatch < 1) Sbatch = 1;
     if (Sbatch > S) Sbatch = S;
     if (Sbatch > 65535) Sbatch = 65535;  // gridDim.z of the table kernel
+    ctx->last_draw_batch = Sbatch;
 
     int rc = ctx->wtab.ensure((size_t)Sbatch * w_per_draw);
     if (rc) return rc;
@@ -263,16 +264,11 @@ int run_loglik_grid_simt(ipn_ctx* ctx, int64_t T, const double* time, const doub
 
     const size_t smem = (size_t)KP * BM * sizeof(float) + (size_t)NST * KC * BN * sizeof(float) +
                         (size_t)J * sizeof(double) + BM * sizeof(double) + 3 * BM * sizeof(float);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[precise ? 1 : 0]) {
-        if (precise)
-            IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                200 * 1024));
-        else
-            IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                200 * 1024));
-        attr_set[precise ? 1 : 0] = true;
-    }
+    // per launch, not cached: the attribute belongs to the (function, device) pair and contexts on several GPUs share this code
+    if (precise)
+        IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    else
+        IPN_CUDA_CHECK(cudaFuncSetAttribute(loglik_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (smem > 200 * 1024) {
         set_error("J = %lld needs %zu bytes of shared memory per CTA (limit 200 KiB)", (long long)J, smem);
         return IPN_ERR_UNSUPPORTED;

@@ -27,9 +27,10 @@
 // Warp roles: 0..15 = epilogue, 16 = bulk-copy producer, 17 / 18 = MMA issuers of the even / odd tiles (17 also does the
 // tcgen05.cp of the W digits).  Three instantiations by epilogue arithmetic (plain fp32 / compensated fp32 / fp64), each
 // working on the draws whose brightness asks for it (tc_draw_kernel decides per draw).
-// Experiment / test hooks read from the environment at every launch: IPN_TC_DEBUG (wait-cycle counters), IPN_TC_SKIP_MATH,
-// IPN_TC_SKIP_MMA, IPN_TC_ONE_ISSUER, IPN_TC_EPI_DELAY, IPN_TC_GRID, IPN_TC_CHUNK_TILES (tests/test_gpu_loglik.py uses them
-// to check that results do not depend on pacing).
+// Experiment / test hooks (IPN_TC_DEBUG wait-cycle counters, IPN_TC_SKIP_MATH, IPN_TC_SKIP_MMA, IPN_TC_ONE_ISSUER,
+// IPN_TC_EPI_DELAY, IPN_TC_GRID, IPN_TC_CHUNK_TILES) exist only in a build with -DIPN_TC_HOOKS (libipn_b200_hooks.so, which
+// tests/test_gpu_loglik.py and tools/ load to check that results do not depend on pacing): the shipped library contains
+// neither the environment look-ups nor the branches.
 #include "loglik_common.cuh"
 #include "loglik_epilogue.cuh"
 #include "tc_perm.cuh"
@@ -48,12 +49,19 @@ struct TcParams {
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
     const int* flags;         // [0] = #bins with counts, [1] = epilogue mode option, [2..3] = sum n_i^2 (double)
+    // the fields below are only read by a -DIPN_TC_HOOKS build (IPN_HOOK())
     int one_issuer;           // experiment switch (IPN_TC_ONE_ISSUER): warp 13 issues every tile, warp 14 only takes part in the hand-shakes
     int epi_delay;            // test hook (IPN_TC_EPI_DELAY, cycles): stall every epilogue unit -> protocol must survive a slow consumer
     int skip_mma;             // experiment switch (IPN_TC_SKIP_MMA): issue one MMA per tile only -> exposes the epilogue-bound period
     int skip_math;            // experiment switch (IPN_TC_SKIP_MATH): epilogue only drains TMEM -> exposes the MMA-bound period
     unsigned long long* dbg;  // optional [grid][8] cycle counters of the pipeline wait sites (NULL = off)
 };
+
+#ifdef IPN_TC_HOOKS
+#define IPN_HOOK(field) (p.field)
+#else
+#define IPN_HOOK(field) 0
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         if (lane == 0) {
             uint32_t tile_seq = 0, item_seq = 0;
             unsigned long long w_be = 0, w_ce = 0;
-            const bool dbg = p.dbg != nullptr;
+            const bool dbg = IPN_HOOK(dbg) != nullptr;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int sl = (int)(item / items_per_draw);
                 if (p.td[sl].hifi != MODE) {
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const uint32_t b_base0 = smem_u32(sB0) >> 4;
         uint32_t tile_seq = 0, item_seq = 0;
         unsigned long long w_af = 0, w_bf = 0, w_te = 0;
-        const bool dbg = p.dbg != nullptr;
+        const bool dbg = IPN_HOOK(dbg) != nullptr;
         const long long t_start = clock64();
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
             if (p.td[(int)(item / items_per_draw)].hifi != MODE) {
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 tc_fence_after();
             }
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                if ((p.one_issuer ? 0u : (tile_seq & 1)) != which) continue;
+                if ((IPN_HOOK(one_issuer) ? 0u : (tile_seq & 1)) != which) continue;
                 const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
                 const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
                 mbar_wait_timed(b_full + st, ph, w_bf, dbg, W_B_FULL, tile_seq, prog);
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     // accumulate into DIFFERENT level accumulators (no back-to-back read-modify-write of one tile).
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
-                        if (p.skip_mma && ks > 0) break;
+                        if (IPN_HOOK(skip_mma) && ks > 0) break;
 #pragma unroll
                         for (int pp = 0; pp < PP; ++pp) {
 #pragma unroll
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_seq = 0;
         unsigned long long w_cf = 0, w_tf = 0;
-        const bool dbg = p.dbg != nullptr;
+        const bool dbg = IPN_HOOK(dbg) != nullptr;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int sl = (int)(item / items_per_draw);
             if (p.td[sl].hifi != MODE) continue;
@@ -491,11 +499,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + tb);
-                    if (p.epi_delay) {
+                    if (IPN_HOOK(epi_delay)) {
                         const long long d0 = clock64();
-                        while (clock64() - d0 < (long long)p.epi_delay * (1 + ((warp * 7 + tile_seq) & 3))) {}
+                        while (clock64() - d0 < (long long)IPN_HOOK(epi_delay) * (1 + ((warp * 7 + tile_seq) & 3))) {}
                     }
-                    if (p.skip_math == 1 || (p.skip_math == 2 && quarter == (MMA_WARP & 3))) {
+                    if (IPN_HOOK(skip_math) == 1 || (IPN_HOOK(skip_math) == 2 && quarter == (MMA_WARP & 3))) {
                         int x = 0;
 #pragma unroll
                         for (int h = 0; h < NH; ++h)
@@ -572,6 +580,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     if (Sbatch < 1) Sbatch = 1;
     if (Sbatch > S) Sbatch = S;
     if (Sbatch > 65535) Sbatch = 65535;
+    ctx->last_draw_batch = Sbatch;
 
     int rc;
     if ((rc = ctx->wtab.ensure((size_t)Sbatch * w_per_draw))) return rc;
@@ -649,7 +658,10 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             // ... and when there are many tiles, so that an item lasts ~0.1 ms: the 32 delay tiles that share a chunk of Phi
             // start up to one item apart (148 CTAs is not a multiple of 32), and the chunk must still be in L2 for the late
             // ones (ncu: 600-tile items re-read half of Phi from HBM, 2.2x the minimum traffic)
-            const int max_tiles = getenv("IPN_TC_CHUNK_TILES") ? atoi(getenv("IPN_TC_CHUNK_TILES")) : 4096 / TN;
+            int max_tiles = 4096 / TN;
+#ifdef IPN_TC_HOOKS
+            if (getenv("IPN_TC_CHUNK_TILES")) max_tiles = atoi(getenv("IPN_TC_CHUNK_TILES"));
+#endif
             if ((n_bt + nchunk - 1) / nchunk > max_tiles) nchunk = (n_bt + max_tiles - 1) / max_tiles;
             const int tiles_per_chunk = (n_bt + nchunk - 1) / nchunk;
             nchunk = (n_bt + tiles_per_chunk - 1) / tiles_per_chunk;
@@ -659,14 +671,18 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             p.G = G; p.Gpad = Gpad; p.a_bytes = a_bytes; p.b_dig = b_dig; p.img_bytes = b_bytes; p.a_plane = a_plane; p.b_plane = b_plane;
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
-            if (getenv("IPN_TC_GRID")) grid = (int)std::min<int64_t>(items, atoi(getenv("IPN_TC_GRID")));  // test hook: several CTA waves
             p.flags = d_nnz;
+            p.skip_math = p.skip_mma = p.epi_delay = p.one_issuer = 0;
+            p.dbg = nullptr;
+            bool want_dbg = false;
+#ifdef IPN_TC_HOOKS
+            if (getenv("IPN_TC_GRID")) grid = (int)std::min<int64_t>(items, atoi(getenv("IPN_TC_GRID")));  // several CTA waves
             p.skip_math = getenv("IPN_TC_SKIP_MATH") ? atoi(getenv("IPN_TC_SKIP_MATH")) : 0;
             p.skip_mma = getenv("IPN_TC_SKIP_MMA") != nullptr;
             p.epi_delay = getenv("IPN_TC_EPI_DELAY") ? atoi(getenv("IPN_TC_EPI_DELAY")) : 0;
             p.one_issuer = getenv("IPN_TC_ONE_ISSUER") != nullptr;
-            p.dbg = nullptr;
-            const bool want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
+            want_dbg = getenv("IPN_TC_DEBUG") != nullptr;
+#endif
             if (want_dbg) {
                 if ((rc = ctx->dbg.ensure((size_t)grid * 8 * sizeof(unsigned long long)))) return rc;
                 IPN_CUDA_CHECK(cudaMemsetAsync(ctx->dbg.p, 0, (size_t)grid * 8 * sizeof(unsigned long long), ctx->stream));

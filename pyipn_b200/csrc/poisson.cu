@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, float a) {
     if (s == 123.456f) out[0] = s;
 }
 
+int run_umma_peak(ipn_ctx* ctx, double* result);  // umma_peak.cu
+
 int run_microbench(ipn_ctx* ctx, int which, double* result) {
+    IPN_REQUIRE(which >= 0 && which <= 2, "ipn_microbench: which must be 0 (FFMA), 1 (MUFU.EX2) or 2 (int8 UTCIMMA)");
+    if (which == 2) return run_umma_peak(ctx, result);
     int rc = ctx->misc.ensure(256);
     if (rc) return rc;
     const int blocks = ctx->sm_count * 8;

@@ -26,11 +26,12 @@ __global__ void __launch_bounds__(RFF_THREADS)
 rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, const double* __restrict__ omega,
                 const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ shift,
                 const double* __restrict__ amp, double* __restrict__ out, int64_t tiles_per_draw) {
-    extern __shared__ double sm[];
-    double* s_w = sm;                                     // [J] omega (fp64: side paths)
-    double* s_a = sm + J;
-    double* s_b = sm + 2 * J;
-    float4* s_f = reinterpret_cast<float4*>(sm + 3 * J);  // [J] (wh, wl, a, b) with w in turns per unit time
+    // the float4 table comes first: behind 3 J doubles it would sit at 8 mod 16 bytes for odd J (misaligned LDS.128)
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    float4* s_f = reinterpret_cast<float4*>(sm_raw);      // [J] (wh, wl, a, b) with w in turns per unit time
+    double* s_w = reinterpret_cast<double*>(s_f + J);     // [J] omega (fp64: side paths)
+    double* s_a = s_w + J;
+    double* s_b = s_w + 2 * J;
     __shared__ unsigned int s_wmax;                       // bits of max_j |wh|
     __shared__ float s_amp2;                              // sum_j a_j^2 + b_j^2 of the draw
     const int64_t n_items = S * tiles_per_draw;
@@ -153,7 +154,10 @@ int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int6
     const int64_t max_grid = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(items < max_grid ? items : max_grid);
     const size_t smem = 3 * (size_t)J * sizeof(double) + (size_t)J * sizeof(float4);
-    const bool full64 = getenv("IPN_RFF_FP64") != nullptr;
+    bool full64 = false;
+#ifdef IPN_TC_HOOKS
+    full64 = getenv("IPN_RFF_FP64") != nullptr;  // hooks build only: every draw through the fp64 side path
+#endif
     if (full64)
         rff_eval_kernel<true><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S, (int)J, omega, a, b, shift, amp,
                                                                          out, tiles);

@@ -32,3 +32,15 @@ def ctx():
     c = Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def hooks_ctx():
+    """Context on the -DIPN_TC_HOOKS build of the library (libipn_b200_hooks.so): the only build in which the pacing /
+    work-skipping environment switches of the hot kernel exist."""
+    from pyipn_b200 import Context
+    from pyipn_b200._lib import HOOKS_LIB_PATH
+
+    c = Context(0, lib_path=HOOKS_LIB_PATH)
+    yield c
+    c.close()

@@ -49,6 +49,20 @@ def test_library_contains_only_sm100a_code():
     assert archs == {"100a"}, archs
 
 
+def test_shipped_library_has_no_experiment_hooks(lib):
+    """The pacing / work-skipping switches of the hot kernel (IPN_TC_*, IPN_RFF_FP64) exist only in the -DIPN_TC_HOOKS build
+    that tests/ and tools/ load explicitly: the product library must not even contain their names."""
+    from pyipn_b200._lib import HOOKS_LIB_PATH, LIB_PATH
+
+    data = open(LIB_PATH, "rb").read()
+    assert b"IPN_TC_" not in data and b"IPN_RFF_FP64" not in data
+    hooks = open(HOOKS_LIB_PATH, "rb").read()
+    assert b"IPN_TC_SKIP_MATH" in hooks and b"IPN_TC_GRID" in hooks
+    hl = ctypes.CDLL(HOOKS_LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(hl, name), name
+
+
 def test_no_cpu_fallback_without_gpu(lib):
     """On a box without a GPU context creation must fail loudly with IPN_ERR_NO_DEVICE, never compute on the host."""
     import torch

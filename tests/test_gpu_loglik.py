@@ -217,13 +217,14 @@ def test_sky_grid_vs_oracle(ctx):
 
 @pytest.mark.parametrize("hook", [{"IPN_TC_GRID": "600"}, {"IPN_TC_GRID": "37"}, {"IPN_TC_EPI_DELAY": "20000"},
                                   {"IPN_TC_CHUNK_TILES": "16"}, {"IPN_TC_ONE_ISSUER": "1"}])
-def test_tc_pipeline_schedule_independence(ctx, monkeypatch, hook):
+def test_tc_pipeline_schedule_independence(hooks_ctx, monkeypatch, hook):
     """The tcgen05 kernel's result must not depend on how its warp roles are paced or its items are cut: several CTA
     waves per SM, fewer CTAs than SMs, an artificially slow epilogue, tiny items, a single MMA issuer.  (A dead-lock in
     the barrier protocol shows up here as a launch failure with the time-out record in the message.)"""
     from pyipn_b200._lib import OPT_LOGLIK_IMPL
     from pyipn_b200.synth import delay_grid_workload
 
+    ctx = hooks_ctx
     w = delay_grid_workload(T=30_000, G=1024, S=6)
     args = (w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
     ctx.set_option(OPT_LOGLIK_IMPL, 2)
@@ -242,12 +243,13 @@ def test_tc_pipeline_schedule_independence(ctx, monkeypatch, hook):
 
 
 @pytest.mark.parametrize("hook", [{"IPN_TC_SKIP_MATH": "1"}, {"IPN_TC_SKIP_MATH": "2"}, {"IPN_TC_SKIP_MMA": "1"}])
-def test_tc_pipeline_survives_unbalanced_roles(ctx, monkeypatch, hook):
+def test_tc_pipeline_survives_unbalanced_roles(hooks_ctx, monkeypatch, hook):
     """Experiment switches that make one role much faster than the others (values are meaningless then): the hand-shakes
     must still complete.  This is the regime in which a skipped barrier phase dead-locked the two-issuer kernel."""
     from pyipn_b200._lib import OPT_LOGLIK_IMPL
     from pyipn_b200.synth import delay_grid_workload
 
+    ctx = hooks_ctx
     w = delay_grid_workload(T=100_000, G=2048, S=8)
     for k, v in hook.items():
         monkeypatch.setenv(k, v)
@@ -257,6 +259,20 @@ def test_tc_pipeline_survives_unbalanced_roles(ctx, monkeypatch, hook):
     finally:
         ctx.set_option(OPT_LOGLIK_IMPL, 0)
     assert ll.shape == (2048, 8)
+
+
+def test_shipped_library_ignores_the_hook_switches(ctx, monkeypatch):
+    """The shipped library has no hooks: IPN_TC_SKIP_MATH in a user's environment must not change a single bit."""
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=6000, G=256, S=3)
+    args = (w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    base = ctx.loglik_delay_grid(*args)
+    monkeypatch.setenv("IPN_TC_SKIP_MATH", "1")
+    monkeypatch.setenv("IPN_TC_SKIP_MMA", "1")
+    got = ctx.loglik_delay_grid(*args)
+    exp = orc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"][::16])
+    assert np.abs(got[::16] - exp).max() < ATOL and np.abs(got - base).max() < 1e-7
 
 
 @pytest.mark.parametrize("boost,comp_guaranteed", [(3_000.0, True), (20_000.0, False)])

@@ -4,11 +4,11 @@ A second argument selects the epilogue (IPN_OPT_HIFI: 2 = plain fp32, the defaul
 import sys
 sys.path.insert(0, ".")
 from pyipn_b200 import Context
-from pyipn_b200._lib import OPT_HIFI
+from pyipn_b200._lib import HOOKS_LIB_PATH, OPT_HIFI
 from pyipn_b200.synth import delay_grid_workload
 S = int(sys.argv[1])
 w = delay_grid_workload(T=100_000, G=4096, S=S)
-ctx = Context(0)
+ctx = Context(0, lib_path=HOOKS_LIB_PATH)  # the -DIPN_TC_HOOKS build: IPN_TC_DEBUG exists only there
 ctx.set_option(OPT_HIFI, int(sys.argv[2]) if len(sys.argv) > 2 else 2)
 for _ in range(2):
     ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])

@@ -4,10 +4,10 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from pyipn_b200 import Context
-from pyipn_b200._lib import OPT_HIFI
+from pyipn_b200._lib import HOOKS_LIB_PATH, OPT_HIFI
 from pyipn_b200.synth import delay_grid_workload
 w = delay_grid_workload(T=100_000, G=4096, S=32)
-ctx = Context(0)
+ctx = Context(0, lib_path=HOOKS_LIB_PATH)  # the -DIPN_TC_HOOKS build: IPN_TC_DEBUG exists only there
 ctx.set_option(OPT_HIFI, 2)
 frac = float((w["counts"] > 0).mean())
 for name, counts in (("as generated (%.0f %% of bins have counts)" % (100 * frac), w["counts"]), ("all bins empty", np.zeros_like(w["counts"])),
