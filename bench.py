@@ -4,11 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (N > 1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on the host cores
 
-Workload (``config.workload``): BASELINE.json config 3 -- 4096 trial delays x posterior draws x 1e5 bins of 1 ms,
-K = 50 RFF features -- sharded by draws, ``--draws-per-gpu`` (default 500 = 4000/8) draws per rank, so N = 8 is
-the full 4096 x 4000 x 1e5 grid and the scaling is weak.  One step = one pass over the rank's shard (delay
-tables, contraction + fused Poisson reduction, finalisation) plus, for N > 1, the all-gather of the
-log-likelihood blocks.  Prints ONE JSON line on rank 0.
+Workload (``config.workload``): BASELINE.json config 3 at full size -- 4096 trial delays x 4000 posterior draws x 1e5
+bins of 1 ms, K = 50 RFF features (1.6384e12 grid-point x bins per step) -- sharded by draws over the ranks, so the
+scaling is STRONG: the total is held at ``--draws`` (default 4000) and every rank evaluates 4000 / N of them.
+``--draws-per-gpu D`` instead fixes the work per rank (weak scaling, D x N draws in total).  One step = one pass over
+the rank's shard (operand images, contraction + fused Poisson reduction, finalisation) plus, for N > 1, the all-gather
+of the log-likelihood blocks.  After the timed loop the TIMED result is spot-checked against the float64 C oracle
+(``parity``: pairs from every internal draw batch of every rank; the run fails above 1e-3 nats).  Prints ONE JSON line
+on rank 0.
 """
 from __future__ import annotations
 
@@ -34,7 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--draws-per-gpu", type=int, default=500)
+    ap.add_argument("--draws", type=int, default=4000, help="total posterior draws, sharded over the ranks (strong scaling)")
+    ap.add_argument("--draws-per-gpu", type=int, default=0, help="> 0: fixed work per rank instead (weak scaling)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="the host-buffer end-to-end loop runs min(steps, this) steps")
+    ap.add_argument("--parity-draws", type=int, default=64, help="most draws in the oracle spot check of the timed result (x 3 delays)")
     ap.add_argument("--delays", type=int, default=4096)
     ap.add_argument("--bins", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=50)
@@ -45,9 +51,15 @@ def parse():
     return ap.parse_args()
 
 
+def total_draws(a, world):
+    return a.draws_per_gpu * world if a.draws_per_gpu > 0 else a.draws
+
+
 def workload_name(a, world):
-    return (f"config3 posterior-predictive sweep shard: {a.delays} delays x {a.draws_per_gpu} draws/GPU x {a.bins} bins, "
-            f"K={a.k} (J={2 * a.k}); {world} rank(s) -> {a.draws_per_gpu * world} draws total")
+    S = total_draws(a, world)
+    how = f"{a.draws_per_gpu} draws per rank (weak)" if a.draws_per_gpu > 0 else f"draws sharded {S}/{world} per rank (strong)"
+    return (f"config3 posterior-predictive sweep: {a.delays} delays x {S} draws x {a.bins} bins, K={a.k} (J={2 * a.k}); "
+            f"{world} rank(s), {how}")
 
 
 class ClockSampler(threading.Thread):
@@ -99,7 +111,7 @@ def run_reference(a, rank, world):
     from oracle.cpu_bench import time_oracle
     from pyipn_b200.synth import delay_grid_workload
 
-    w = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, a.draws_per_gpu), k=a.k)
+    w = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, total_draws(a, world)), k=a.k)
     cores = os.cpu_count() or 1
     vals, secs = [], []
     for step in range(a.warmup + a.steps):
@@ -111,12 +123,61 @@ def run_reference(a, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": "RFF Poisson loglik grid-points*bins/s", "value": v, "unit": "grid-point*bins/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if a.draws_per_gpu > 0 else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": workload_name(a, world), "step": r["sample"]},
         "cpu_baseline": {"value": v, "unit": "grid-point*bins/s", "cores": cores, "kind": "port", "sample": r["sample"]},
         "e2e": {"value": v, "unit": "grid-point*bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def parity_check(a, w, full, S_total, world, batch):
+    """Oracle spot check of the result the TIMED loop produced (``full``: (G, S_total), all ranks' shards gathered).
+
+    Draws: one of every internal draw batch of the library on every rank (``batch`` draws each: the operand-image scratch
+    is bounded, so a shard is processed in several batches) and both ends of the draw range, at least 24; delays: the first draw's best delay, its neighbour and one far away.  The checker is the float64 plain-C
+    restatement of rff.py + functions.stan:23-35 (oracle/ipn_oracle.c) on the host cores.  Tolerance: 1e-3 nats absolute
+    (north star).  Also: on four draws the oracle's arg-max over a +-2 window around the device's arg-max must be the
+    device's arg-max."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import shard_bounds
+
+    G = full.shape[0]
+    picks, n_batches = {0, S_total - 1}, 0
+    for r in range(world):
+        lo, hi = shard_bounds(S_total, r, world)
+        for b0 in range(lo, hi, batch):
+            picks.add(b0 if n_batches % 2 == 0 else min(hi, b0 + batch) - 1)  # one draw of EVERY batch, first / last alternating
+            n_batches += 1
+    picks = sorted(picks)
+    if len(picks) > a.parity_draws:  # more batches than the budget: an even subsample, ends kept
+        keep = np.unique(np.linspace(0, len(picks) - 1, a.parity_draws).round().astype(int))
+        picks = [picks[i] for i in keep]
+    extra = [s for s in range(0, S_total, max(1, S_total // max(1, a.parity_draws))) if s not in picks]
+    picks = sorted(set(picks + extra[: max(0, min(a.parity_draws, 24) - len(picks))]))
+    best0 = int(np.argmax(full[:, picks[0]]))
+    gsel = sorted({best0, min(G - 1, best0 + 1), (best0 + G // 2) % G})
+    args = lambda idx: (w["counts"], w["time"], w["exposure"], w["omega"][idx], w["a"][idx], w["b"][idx], w["amp"][idx], w["bkg"][idx])
+    t0 = time.perf_counter()
+    exp = corc.loglik_delay_grid(*args(picks), w["delays"][gsel])
+    got = full[np.ix_(gsel, picks)]
+    err = float(np.abs(got - exp).max())
+    # arg-max on a window around the device's maximum, four draws spread over the range
+    am_draws = [picks[i] for i in sorted({0, len(picks) // 3, 2 * len(picks) // 3, len(picks) - 1})]
+    argmax_equal = True
+    for s in am_draws:
+        b = int(np.argmax(full[:, s]))
+        win = np.arange(max(0, b - 2), min(G, b + 3))
+        e = corc.loglik_delay_grid(*args([s]), w["delays"][win])[:, 0]
+        argmax_equal &= bool(win[int(np.argmax(e))] == b)
+        err = max(err, float(np.abs(full[win, s] - e).max()))
+    tol = 1e-3
+    return {"checker": "oracle/ipn_oracle.c (float64 restatement of rff.py + functions.stan:23-35), timed result of the resident loop",
+            "pairs": int(len(gsel) * len(picks) + 5 * len(am_draws)), "draws_checked": len(picks), "delays_checked": gsel,
+            "draw_batches_of_the_library": n_batches, "draws_per_batch": int(batch), "max_abs_nats": err, "tol": tol,
+            "argmax_equal": bool(argmax_equal), "argmax_draws": am_draws, "ok": bool(err < tol and argmax_equal),
+            "seconds": time.perf_counter() - t0}
 
 
 def main():
@@ -156,7 +217,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    S_total = a.draws_per_gpu * world
+    S_total = total_draws(a, world)
     w = delay_grid_workload(T=a.bins, G=a.delays, S=S_total, k=a.k)
     lo, hi = shard_bounds(S_total, rank, world)
     S = hi - lo
@@ -167,8 +228,13 @@ def main():
     ll = torch.empty((G, S), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # everything of the step -- L2 flush, library kernels, all-gather -- is enqueued on ONE explicit stream whose handle the
+    # library borrows, so the flush is ordered before the kernels and the gather after them (torch's default stream is
+    # the legacy stream, handle 0; passing an explicit stream leaves no room for an ordering accident)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.set_option(OPT_LOGLIK_IMPL, a.loglik_impl)
     if a.epilogue:
         ctx.set_option(OPT_HIFI, a.epilogue)
@@ -211,6 +277,7 @@ def main():
     ev1.record()
     barrier()
     trace("timed region closed")
+    timed_full = full.clone()  # the result the timed loop produced (the e2e loop below overwrites nothing of it, but keep it apart)
     clocks = sampler.stop() if sampler else None
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
@@ -234,11 +301,12 @@ def main():
             return gather_columns(out_pinned.to(dev, non_blocking=True), S_total)
         return out_pinned
 
+    e2e_steps = max(1, min(a.steps, a.e2e_steps))
     step_e2e()
     barrier()
     trace("e2e warm-up done")
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(e2e_steps):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -249,8 +317,10 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in pinned.values()) * world
     d2h = out_pinned.numel() * out_pinned.element_size() * world
 
-    # parity spot check of the timed result against the e2e result (same inputs, two entry points)
+    # the two entry points must agree (same inputs); the check against the ORACLE is below
     same = bool(torch.allclose(ll.cpu(), out_pinned, rtol=0, atol=1e-6))
+    batch = max(1, ctx.last_draw_batch)
+    parity = parity_check(a, w, timed_full.cpu().numpy(), S_total, world, batch) if rank == 0 else None
 
     if rank == 0:
         peaks = {}
@@ -283,11 +353,20 @@ def main():
         if impl == 2:
             # tcgen05 back-end: 9 int8 digit-plane products x 224 K rows = 2016 MAC = 4032 int8 op per unit
             ops = units_timed * 4032.0 / main_s / 1e12 if main_ms > 0 else None
-            bf16 = float(peaks.get("bf16_tflops", 1590.0))
-            peak = 2.0 * bf16
-            roof = {"bound": "tensor", "achieved": ops, "peak": peak, "unit": "TOP/s (int8)", "frac": ops / peak if ops else None,
-                    "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst, measured): no int8 figure is measured on this pool; "
-                                    "nominal dense int8 is 2 x bf16" if "bf16_tflops" in peaks else "2 x fallback 1590 TF/s bf16"),
+            # denominators: (i) the int8 tensor pipe as this kernel's MMA shape can drive it, MEASURED in this process right
+            # after the timed region (ipn_microbench 2: back-to-back tcgen05.mma kind::i8 M128 N32 K32, A in tensor memory, on
+            # every SM, timed with CUDA events -> at the clock the chip holds under that load); (ii) 2 x the bf16 figures
+            # of MEASURED_PEAKS.json (dense int8 is nominally 2 x bf16; no int8 number is measured for this pool)
+            int8_measured = ctx.microbench(2)
+            bf16_burst = peaks.get("bf16_tflops")
+            bf16_sust = peaks.get("bf16_tflops_sustained")
+            roof = {"bound": "tensor", "achieved": ops, "peak": int8_measured, "unit": "TOP/s (int8)",
+                    "frac": ops / int8_measured if ops else None,
+                    "peak_source": "measured in this run: ipn_microbench(2), tcgen05.mma kind::i8 issue loop (M128 N32 K32, A from TMEM) on all SMs",
+                    "frac_of_2x_bf16_sustained": ops / (2.0 * bf16_sust) if ops and bf16_sust else None,
+                    "frac_of_2x_bf16_burst": ops / (2.0 * bf16_burst) if ops and bf16_burst else None,
+                    "peaks_file": {"bf16_tflops": bf16_burst, "bf16_tflops_sustained": bf16_sust,
+                                   "note": "MEASURED_PEAKS.json (driver-written)" if peaks else "MEASURED_PEAKS.json absent"},
                     "algorithmic_op_per_unit": 4032.0}
         else:
             roof = {"bound": "fp32", "achieved": fp32_equiv, "peak": fp32_nominal, "unit": "TFLOP/s",
@@ -297,21 +376,21 @@ def main():
         line = {
             "metric": "RFF Poisson loglik grid-points*bins/s", "value": value, "unit": "grid-point*bins/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "weak" if a.draws_per_gpu > 0 else "strong", "vs_baseline": None,
             "dtype": "int8 digit planes -> int32 (exact) + f32 epilogue, f64 phases/reduction" if impl == 2 else "f32 contraction, f64 phases/reduction",
             "data": "synthetic",
             "config": {"workload": workload_name(a, world), "l2": "256 MiB memset between steps, inside the timed region",
                        "loglik_impl": {0: "auto", 1: "fp32-pipe", 2: "tcgen05"}[a.loglik_impl] + f" -> ran {impl}", "seed": 20261019,
                        **({"epilogue": a.epilogue} if a.epilogue else {})},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": units_step * a.steps / e2e_s, "unit": "grid-point*bins/s", "h2d_bytes_per_step": int(h2d),
+            "e2e": {"value": units_step * e2e_steps / e2e_s, "steps": e2e_steps, "unit": "grid-point*bins/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "timer": "host perf_counter, max over ranks", "matches_resident": same},
-            "roofline": roof,
+            "roofline": roof, "parity": parity,
         }
         if world == 1 and not a.no_cpu_baseline:
             from oracle.cpu_bench import time_oracle
 
-            small = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, a.draws_per_gpu), k=a.k)
+            small = delay_grid_workload(T=a.bins, G=a.delays, S=min(8, S_total), k=a.k)
             r = time_oracle(small)
             line["cpu_baseline"] = {"value": r["value"], "unit": "grid-point*bins/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
@@ -319,6 +398,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py: the timed result is off the oracle by {parity['max_abs_nats']:.3g} nats (tolerance {parity['tol']})")
 
 
 if __name__ == "__main__":

@@ -359,3 +359,58 @@ def test_delay_grid_random_small_shapes_property(ctx, impl):
         ctx.set_option(OPT_LOGLIK_IMPL, 0)
     z = np.zeros((1, 109))
     assert ctx.loglik_delay_grid(np.arange(4.0), np.ones(4), np.zeros(4, dtype=np.int64), z, z, z, [1.0], [1.0], [0.0]).shape == (1, 1)
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_draw_batches_are_stitched_correctly(ctx, impl):
+    """The library works through the draws in internal batches (bounded operand-image scratch).  With IPN_OPT_DRAW_BATCH = 2
+    and S = 5 the call crosses two batch boundaries and ends on a ragged batch: every draw must match the oracle
+    (functions.stan:23-35 composed with fit.py:671-691) and the un-batched call bit for bit (each draw's arithmetic does not
+    depend on its batch)."""
+    from pyipn_b200._lib import OPT_DRAW_BATCH, OPT_LOGLIK_IMPL
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=7001, G=200, S=5)
+    args = (w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    ctx.set_option(OPT_LOGLIK_IMPL, impl)
+    try:
+        whole = ctx.loglik_delay_grid(*args)
+        assert ctx.last_draw_batch == 5
+        ctx.set_option(OPT_DRAW_BATCH, 2)
+        got = ctx.loglik_delay_grid(*args)
+        assert ctx.last_draw_batch == 2
+    finally:
+        ctx.set_option(OPT_DRAW_BATCH, 0)
+        ctx.set_option(OPT_LOGLIK_IMPL, 0)
+    exp = orc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    assert np.abs(got - exp).max() < ATOL
+    np.testing.assert_array_equal(np.argmax(got, axis=0), np.argmax(exp, axis=0))
+    if impl == 2:  # the sliced-integer contraction is exact and the per-thread sums are deterministic per (draw, delay)
+        np.testing.assert_allclose(got, whole, rtol=0, atol=2e-9)
+
+
+def test_many_draws_full_length_vs_oracle(ctx):
+    """Bench shape in the draw and bin dimensions (S = 200 > one internal batch of ~85 draws, T = 1e5, fewer delays): a
+    subsample of (delay, draw) pairs from EVERY internal batch, including their first and last draws, against the C oracle
+    at 1e-3 nats, per-draw arg-max on a window around the device's maximum."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.synth import delay_grid_workload
+
+    corc.build()
+    S, G = 200, 512
+    w = delay_grid_workload(T=100_000, G=G, S=S)
+    ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    batch = ctx.last_draw_batch
+    assert 1 <= batch < S, "the call must span several internal batches for this test to mean anything"
+    draws = sorted({0, S - 1, *range(0, S, batch), *(min(S, b + batch) - 1 for b in range(0, S, batch)), 17, 101})
+    best = int(np.argmax(ll[:, 0]))
+    gsel = sorted({0, best, min(G - 1, best + 1), G - 1})
+    exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"][draws], w["a"][draws], w["b"][draws],
+                                 w["amp"][draws], w["bkg"][draws], w["delays"][gsel])
+    assert np.abs(ll[np.ix_(gsel, draws)] - exp).max() < ATOL
+    for s in (draws[1], draws[-2]):
+        b = int(np.argmax(ll[:, s]))
+        win = np.arange(max(0, b - 2), min(G, b + 3))
+        e = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"][[s]], w["a"][[s]], w["b"][[s]],
+                                   w["amp"][[s]], w["bkg"][[s]], w["delays"][win])[:, 0]
+        assert win[int(np.argmax(e))] == b
