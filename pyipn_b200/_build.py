@@ -14,12 +14,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libipn_b200.so")
+# IPN_BUILD_TAG=<tag> (with IPN_NVCC_EXTRA=<flags>): an experimental variant next to the product library
+# (libipn_b200_<tag>.so, objects in csrc/build_<tag>/), selected at run time with IPN_B200_LIB=<path>; kernel A/B timing only
+TAG = os.environ.get("IPN_BUILD_TAG", "")
+LIB = os.path.join(HERE, f"libipn_b200{'_' + TAG if TAG else ''}.so")
 # the same library with the experiment / test hooks of the hot kernel compiled in (-DIPN_TC_HOOKS: environment switches that
 # re-pace the pipeline or skip work); only tests/ and tools/ load it, the shipped library has none of it
-HOOKS_LIB = os.path.join(HERE, "libipn_b200_hooks.so")
+HOOKS_LIB = os.path.join(HERE, f"libipn_b200{'_' + TAG if TAG else ''}_hooks.so")
 HOOKS_SOURCES = ["loglik_tc.cu", "rff_eval.cu"]  # the translation units that contain hooks
-OBJDIR = os.path.join(CSRC, "build")
+OBJDIR = os.path.join(CSRC, "build" + ("_" + TAG if TAG else ""))
 
 SOURCES = ["ipn_api.cu", "rff_eval.cu", "loglik_prep.cu", "loglik_simt.cu", "loglik_tc.cu", "poisson.cu", "correlate.cu", "binning.cu", "thinning.cu", "sky_post.cu", "umma_peak.cu"]
 

@@ -196,6 +196,7 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
     ctx->accum.release();
     ctx->misc.release();
     ctx->tcdraw.release();
+    ctx->phitab.release();
     ctx->dbg.release();
     ctx->perm.release();
     for (auto& s : ctx->io) s.release();

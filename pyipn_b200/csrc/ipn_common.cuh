@@ -72,6 +72,7 @@ struct ipn_ctx {
     ipn::Scratch perm;     // bin permutation (counts > 0 first) of the tcgen05 path
     ipn::Scratch dbg;      // pipeline wait counters (IPN_TC_DEBUG)
     ipn::Scratch tcdraw;   // per-draw scale factors of the tcgen05 path
+    ipn::Scratch phitab;   // 1024-point fixed-point unit circle of the Phi image kernel (built on first use)
     void* pinned = nullptr;  // pinned host bounce buffer
     size_t pinned_cap = 0;
 };

@@ -71,19 +71,24 @@ __device__ __forceinline__ float exp2_poly(float x) {
     return exp2_core(x - (t - kMagic), t);
 }
 
-// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04.  The upper clamp
-// keeps 1 + u below 2^121 so that the log refinement below needs no clamp of its own.
-__device__ __forceinline__ float exp2_hilo(float xh, float xl) {
-    xh = fminf(fmaxf(xh, -125.0f), 120.0f);
-    const float t = xh + kMagic;
-    return exp2_core((xh - (t - kMagic)) + xl, t);
-}
-
-// The same without the clamps, for callers that have bounded the exponent themselves (|xh + xl| <= 120: the product
-// epilogue is only selected for draws with |c| + log2e sum_j |(a_j, b_j)| <= 120, tc_draw_kernel).
+// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04, for |xh + xl| <= 120: no clamps.
+// The tcgen05 path bounds the exponent per draw instead (tc_draw_kernel: |c| + log2e sum_j |(a_j, b_j)| <= 120, ~40 for a draw
+// of the prior; a draw beyond the bound goes to the fp64 epilogue, whose exp2 needs none), which saves the two FMNMX of
+// every (delay, bin).  The bound also keeps 1 + u below 2^121, so the log refinement below needs no clamp of its own.
+// -DIPN_EPI_CLAMP restores the clamped form (A/B timing).
 __device__ __forceinline__ float exp2_hilo_bounded(float xh, float xl) {
     const float t = xh + kMagic;
     return exp2_core((xh - (t - kMagic)) + xl, t);
+}
+// the clamped form, for callers without a per-draw bound (the FP32-pipe kernel)
+__device__ __forceinline__ float exp2_hilo_clamped(float xh, float xl) {
+    return exp2_hilo_bounded(fminf(fmaxf(xh, -125.0f), 120.0f), xl);
+}
+__device__ __forceinline__ float exp2_hilo(float xh, float xl) {
+#ifdef IPN_EPI_CLAMP
+    xh = fminf(fmaxf(xh, -125.0f), 120.0f);
+#endif
+    return exp2_hilo_bounded(xh, xl);
 }
 
 // One bin's contribution in base-2 units:  n log2(1 + u) - (khi + klo) u  as a main part (ONE rounding of the
@@ -165,6 +170,52 @@ __device__ __forceinline__ bool sincos_phase_df(float wh, float wl, float th, fl
     const float cross = fmaf(wh, tl, fmaf(wl, th, e));
     const float k = (ph + 12582912.0f) - 12582912.0f;
     sincos_turns(ph - k, cross, s, c);
+    return true;
+}
+
+// ---- Phi in fixed point: (sin, cos)(2 pi w t) as integers scaled by 2^30 (the four 8-bit digit planes of the tcgen05 path) ----
+// A float result (24 bits, 2e-8 rms from the polynomial) limits Phi to ~2^-23; what the digit planes need is 2^-31.  Instead
+// of a longer polynomial in higher precision: a table of the 1024 points k/1024 of the unit circle in 2^-30 fixed point
+// (built once per context in float64, 8 KB, staged in shared memory by the image kernel) plus a first-order rotation by
+// the remainder, |theta| <= 2 pi / 2048 = 3.07e-3:
+//   sin(a + theta) = s + (s dc + c ds),  cos(a + theta) = c + (c dc - s ds),  ds = theta - theta^3 / 6,  dc = -theta^2 / 2
+// (theta^4 / 24 = 3.7e-12 and theta^5 / 120 are below 2^-31 and dropped).  The bracket is at most 3.1e-3, so its fp32
+// evaluation is good to ~2e-10 absolute; it is rounded to an integer by a magic-number add and added to the table entry in
+// the same IADD3.  About 30 instructions per (sin, cos) pair including the phase reduction -- fewer than the 37 of the fp32
+// polynomial route it replaces -- and no fp64 instruction.
+constexpr int kPhiTabSize = 1024;
+struct PhiTabEntry {
+    int s, c;  // llrint(sin(2 pi k / 1024) 2^30), llrint(cos(2 pi k / 1024) 2^30)
+};
+
+// fh in [-1/2, 1/2] turns (exact), cross a small correction in turns (sincos_phase_df's split)
+__device__ __forceinline__ void sincos_turns_q30(float fh, float cross, const PhiTabEntry* __restrict__ tab, int& qs, int& qc) {
+    // table point nearest to fh + cross (at |phase| ~ 1e4 turns the correction is itself a table step wide, so it must take part
+    // in the choice; the rounding of this sum only decides between neighbouring points, the remainder below is exact)
+    const float t = fmaf(fh + cross, 1024.0f, kMagic);         // low mantissa bits: rint(1024 (fh + cross))
+    const float kf = t - kMagic;
+    const PhiTabEntry e = tab[__float_as_int(t) & (kPhiTabSize - 1)];  // kMagicBits is a multiple of 1024: two's-complement index
+    const float fl = fmaf(kf, -0.0009765625f, fh) + cross;     // first part exact, |fl| <= 2^-11 (+ cross)
+    const float th = fmaf(fl, 6.2831854820251465f, fl * -1.7484555e-07f);  // radians, 2 pi as fp32 hi + lo
+    const float th2 = th * th;
+    const float ds = fmaf(th2 * th, -0.16666667f, th);
+    const float dc = -0.5f * th2;
+    const float sf = (float)e.s, cf = (float)e.c;              // table values scaled by 2^30 (24 bits are plenty for the bracket)
+    const float rs = fmaf(sf, dc, cf * ds) + kMagic;           // |bracket| <= 3.4e6 < 2^22: the magic-number add rounds it
+    const float rc = fmaf(cf, dc, -(sf * ds)) + kMagic;
+    qs = e.s + (__float_as_int(rs) - kMagicBits);
+    qc = e.c + (__float_as_int(rc) - kMagicBits);
+}
+
+// (sin, cos)(2 pi (wh + wl)(th + tl)) scaled by 2^30; false if the phase is too large for the fp32 split (caller: fp64 route)
+__device__ __forceinline__ bool sincos_phase_q30(float wh, float wl, float th, float tl, const PhiTabEntry* __restrict__ tab,
+                                                 int& qs, int& qc) {
+    const float ph = wh * th;
+    if (!(fabsf(ph) < 4194304.0f)) return false;
+    const float e = fmaf(wh, th, -ph);
+    const float cross = fmaf(wh, tl, fmaf(wl, th, e));
+    const float k = (ph + kMagic) - kMagic;
+    sincos_turns_q30(ph - k, cross, tab, qs, qc);
     return true;
 }
 

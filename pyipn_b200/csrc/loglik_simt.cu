@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(simt::NTHREADS, 3) loglik_simt_kernel(const Si
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float l;
-                        cs[q] += (double)poisson_term(exp2_hilo(acc[r][q] + dcs.c_hi, 0.0f), n, n * 1.44269504f, khi, klo, l);
+                        cs[q] += (double)poisson_term(exp2_hilo_clamped(acc[r][q] + dcs.c_hi, 0.0f), n, n * 1.44269504f, khi, klo, l);
                         lo[q] += l;
                     }
                 }

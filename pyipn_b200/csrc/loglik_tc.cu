@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* a_empty = bars + 1;
     uint64_t* t_empty = bars + 2;            // [NBUF]
     uint64_t* t_full = t_empty + NBUF;       // [NTF]
-    uint64_t* b_full = t_full + NTF;         // [NBST]
-    uint64_t* b_empty = b_full + NBST;       // [NBST]
+    uint64_t* b_full = t_full + NTF;         // [NBFULL]: indexed by tile % NBFULL so that each barrier belongs to ONE issuer
+    uint64_t* b_empty = b_full + NBFULL;     // [NBST]
     uint64_t* c_full = b_empty + NBST;       // [NCST]
     uint64_t* c_empty = c_full + NCST;       // [NCST]
     uint64_t* a_tmem_full = c_empty + NCST;  // W digits of the current item are in tensor memory (issuer 0 -> issuer 1)
@@ -281,10 +281,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_tmem_free, 2);
         for (int i = 0; i < NBUF; ++i) mbar_init(t_empty + i, EPI_ARRIVALS);
         for (int i = 0; i < NTF; ++i) mbar_init(t_full + i, 1);
-        for (int i = 0; i < NBST; ++i) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
-        }
+        for (int i = 0; i < NBFULL; ++i) mbar_init(b_full + i, 1);
+        for (int i = 0; i < NBST; ++i) mbar_init(b_empty + i, 1);
         for (int i = 0; i < NCST; ++i) {
             mbar_init(c_full + i, 1);
             mbar_init(c_empty + i, EPI_ARRIVALS);
@@ -327,8 +325,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     const uint8_t* img = p.Pimg + ((int64_t)sl * p.n_bt + bt) * p.img_bytes;
                     const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
                     mbar_wait_relaxed(b_empty + st, ph ^ 1, W_B_EMPTY, tile_seq, prog);  // released by the MMA commit
-                    mbar_expect_tx(b_full + st, p.b_dig);
-                    bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + st);
+                    mbar_expect_tx(b_full + tile_seq % NBFULL, p.b_dig);
+                    bulk_g2s(sB0 + (size_t)st * p.b_dig, img, p.b_dig, b_full + tile_seq % NBFULL);
                     const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
                     mbar_wait_relaxed(c_empty + cs, cph ^ 1, W_C_EMPTY, tile_seq, prog);  // released by the epilogue warps
                     mbar_expect_tx(c_full + cs, CONST_BYTES);
@@ -390,9 +388,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             }
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 if ((IPN_HOOK(one_issuer) ? 0u : (tile_seq & 1)) != which) continue;
-                const uint32_t st = tile_seq % NBST, ph = (tile_seq / NBST) & 1;
+                const uint32_t st = tile_seq % NBST;
                 const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
-                mbar_wait_timed(b_full + st, ph, w_bf, dbg, W_B_FULL, tile_seq, prog);
+                mbar_wait_timed(b_full + tile_seq % NBFULL, (tile_seq / NBFULL) & 1, w_bf, dbg, W_B_FULL, tile_seq, prog);
                 mbar_wait_timed(t_empty + tb, tph ^ 1, w_te, dbg, W_T_EMPTY, tile_seq, prog);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + ACC_COL0 + tb * (NLEV * TN);
@@ -555,6 +553,17 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     }
 }
 
+// the 1024-point fixed-point unit circle of tc_pimg_kernel, built on first use (8 KB, lives as long as the context)
+static int ensure_phitab(ipn_ctx* ctx) {
+    if (ctx->phitab.p) return IPN_OK;
+    int rc = ctx->phitab.ensure(kPhiTabSize * sizeof(PhiTabEntry));
+    if (rc) return rc;
+    tc_phitab_kernel<<<kPhiTabSize / 256, 256, 0, ctx->stream>>>(ctx->phitab.as<PhiTabEntry>());
+    ctx->launches += 1;
+    IPN_CUDA_CHECK(cudaGetLastError());
+    return IPN_OK;
+}
+
 bool tc_supported(int64_t J) { return 2 * J + tc::MIN_CROWS <= tc::KPAD_MAX; }
 
 int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
@@ -567,12 +576,14 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     }
     const int Kpad = (int)(((2 * J + MIN_CROWS + 31) / 32) * 32);
     const int ksteps = Kpad / 32;
+    int rc0;
     const int n_dt = (int)((G + TM - 1) / TM);
     const int64_t Gpad = (int64_t)n_dt * TM;
     const int n_bt = (int)((T + TN - 1) / TN);
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
-    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + 2 * NBST + 2 * NCST) * 8 + 16 + 24 * 4;
+    if ((rc0 = ensure_phitab(ctx))) return rc0;
+    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + NBFULL + NBST + 2 * NCST) * 8 + 16 + 24 * 4;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -640,7 +651,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                                                                             n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
             tc_pimg_kernel<<<dim3(n_bt, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
-                                                                     omega, d_dc, d_td, n_bt, b_bytes, b_plane, d_P);
+                                                                     omega, d_dc, d_td, ctx->phitab.as<PhiTabEntry>(), n_bt, b_bytes, b_plane, d_P);
         ctx->launches += 3;
         IPN_CUDA_CHECK(cudaGetLastError());
 

@@ -16,7 +16,11 @@ constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
 constexpr int TN = IPN_TC_TN; // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
 constexpr int PW = 4;         // W digit planes
-constexpr int PP = 3;         // Phi digit planes
+#ifndef IPN_TC_PP
+#define IPN_TC_PP 4
+#endif
+constexpr int PP = IPN_TC_PP; // Phi digit planes: 4 = Phi to 2^-31 (default), 3 = to 2^-23 (-DIPN_TC_PP=3: the round-1 layout, kept for A/B timing)
+static_assert(PP == 3 || PP == 4, "Phi has three or four digit planes");
 #ifndef IPN_TC_EPI_WARPS
 #define IPN_TC_EPI_WARPS 16
 #endif
@@ -50,8 +54,12 @@ constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after 
 constexpr int NCST = (6 % OWN_PERIOD == 0) ? 6 : 2 * OWN_PERIOD;  // depth of the shared-memory ring of those constant blocks
 constexpr int NTF = NCST;                  // "accumulators complete" barriers: tile % NTF
 static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
-constexpr int NBST = 128 / TN;             // depth of the Phi digit-plane ring (4 tiles of 32 bins: 86 KB)
+constexpr int NBST = (PP == 4 ? 96 : 128) / TN;  // depth of the Phi digit-plane ring (3 tiles of 32 bins x 4 planes, or 4 x 3 planes: 86 KB)
 constexpr int NBUF = 256 / (NLEV * TN);    // accumulator buffers in TMEM columns [256, 512)
+constexpr int NBFULL = (NBST % 2 == 0) ? NBST : 2 * NBST;  // "stage filled" barriers: tile % NBFULL.  The two MMA issuers take
+                                           // alternate tiles, and a parity wait is only sound if the waiter sees every phase of
+                                           // its barrier: with an odd ring depth a stage alternates between the issuers, so the
+                                           // barriers (not the stages) are doubled and each one belongs to one issuer
 static_assert(NBUF >= 2 && NBUF % 2 == 0 && NTF >= NBUF, "each accumulator buffer belongs to one issuer");
 constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
 }  // namespace tc
@@ -104,7 +112,11 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     // fp32 epilogue would get, provided no exponent can leave [-120, 120] (|x| <= |c| + log2e sum_j |(a_j, b_j)|, the phases
     // of all frequencies aligned; ~40 for a draw of the prior): that epilogue evaluates 2^x without clamps.  The other
     // draws keep the automatic choice.
-    if (flags[1] == 4 && t.hifi == 0 && (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0) t.hifi = 3;
+    const bool bounded = (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0;
+    if (flags[1] == 4 && t.hifi == 0 && bounded) t.hifi = 3;
+    // the fp32 epilogues evaluate 2^x without clamps (exp2_hilo): a draw whose exponent could leave [-120, 120] -- amplitudes
+    // far outside anything the model's priors produce -- is evaluated by the fp64 epilogue whatever the option says
+    if (!bounded) t.hifi = 2;
     t.pad = 0;
     td[sl] = t;
 }
@@ -159,14 +171,27 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
 }
 
 
-// Phi digit planes + Poisson constants of one (draw, tile of 64 permuted bins).
+// The 1024-point unit circle in 2^-30 fixed point (loglik_common.cuh: sincos_turns_q30), built once per context in float64.
+__global__ void tc_phitab_kernel(PhiTabEntry* __restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kPhiTabSize) return;
+    const double ang = 6.283185307179586476925 * (double)k / (double)kPhiTabSize;
+    PhiTabEntry e;
+    e.s = (int)llrint(sin(ang) * 1073741824.0);
+    e.c = (int)llrint(cos(ang) * 1073741824.0);
+    tab[k] = e;
+}
+
+// Phi digit planes + Poisson constants of one (draw, tile of TN permuted bins).
 // 256 threads: row = tid % 32, eight threads per row interleave the 16-wide K chunks.
+// Phi = (p1 2^24 + p2 2^16 + p3 2^8 + p4) 2^-30 with the sine / cosine formed directly in 2^-30 fixed point (PP = 4), or the
+// round-1 variant (p1 2^16 + p2 2^8 + p3) 2^-22 from fp32 polynomials (PP = 3); p1 is the same digit in both.
 __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
                                                       const double* __restrict__ exposure, const int64_t* __restrict__ counts,
                                                       const int* __restrict__ perm, const int* __restrict__ n_nz,
                                                       const double* __restrict__ omega, const DrawConst* __restrict__ dc,
-                                                      const TcDraw* __restrict__ td, int n_bt, uint32_t b_bytes, uint32_t b_plane,
-                                                      uint8_t* __restrict__ Pimg) {
+                                                      const TcDraw* __restrict__ td, const PhiTabEntry* __restrict__ phitab, int n_bt,
+                                                      uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
     const int row = threadIdx.x & (tc::TN - 1);
     const int kg = threadIdx.x / tc::TN;
     const int bt = blockIdx.x;
@@ -178,37 +203,58 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
     const double t = valid ? time[i] : 0.0;
     const float th = (float)t, tl = (float)(t - (double)(float)t);
     uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
-    // omega / 2 pi of this draw as fp32 hi + lo: the phases are formed without fp64 arithmetic (sincos_phase_df)
+    // omega / 2 pi of this draw as fp32 hi + lo: the phases are formed without fp64 arithmetic (sincos_phase_df / _q30)
     __shared__ float2 s_w[IPN_MAX_J];
+    __shared__ PhiTabEntry s_tab[tc::PP == 4 ? kPhiTabSize : 1];
     for (int j = threadIdx.x; j < J; j += 256) {
         const double wt = omega[s * J + j] * 0.15915494309189534561;
         const float wh = (float)wt;
         s_w[j] = make_float2(wh, (float)(wt - (double)wh));
     }
+    if (tc::PP == 4)
+        for (int k = threadIdx.x; k < kPhiTabSize; k += 256) s_tab[k] = phitab[k];
     __syncthreads();
     for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
-        alignas(16) int8_t d[3][16];
+        alignas(16) int8_t d[tc::PP][16];
 #pragma unroll
         for (int kk = 0; kk < 16; kk += 2) {
             const int k = kc * 16 + kk;
             int q0 = 0, q1 = 0;
-            if (valid) {
-                if (k < 2 * J) {
-                    float sn, cn;
-                    const float2 w = s_w[k >> 1];
-                    if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
-                    q0 = __float2int_rn(cn * 4194304.0f);  // cos row
-                    q1 = __float2int_rn(sn * 4194304.0f);  // sin row
-                } else {
-                    q0 = q1 = 4194304;  // constant rows: Phi = 1
+            if (tc::PP == 4) {
+                if (valid) {
+                    if (k < 2 * J) {
+                        const float2 w = s_w[k >> 1];
+                        if (!sincos_phase_q30(w.x, w.y, th, tl, s_tab, q1, q0)) {
+                            double sn, cn;
+                            sincos(omega[s * J + (k >> 1)] * t, &sn, &cn);
+                            q0 = (int)llrint(cn * 1073741824.0);
+                            q1 = (int)llrint(sn * 1073741824.0);
+                        }
+                    } else {
+                        q0 = q1 = 1073741824;  // constant rows: Phi = 1
+                    }
                 }
+                split_digits4(q0, d[0][kk], d[1][kk], d[2][kk], d[tc::PP - 1][kk]);
+                split_digits4(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[tc::PP - 1][kk + 1]);
+            } else {
+                if (valid) {
+                    if (k < 2 * J) {
+                        float sn, cn;
+                        const float2 w = s_w[k >> 1];
+                        if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
+                        q0 = __float2int_rn(cn * 4194304.0f);  // cos row
+                        q1 = __float2int_rn(sn * 4194304.0f);  // sin row
+                    } else {
+                        q0 = q1 = 4194304;  // constant rows: Phi = 1
+                    }
+                }
+                int8_t dummy;
+                split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
+                split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
             }
-            int8_t dummy;
-            split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
-            split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
         }
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
+        for (int pl = 0; pl < tc::PP; ++pl)
             *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
                 *reinterpret_cast<const int4*>(d[pl]);
     }
@@ -232,13 +278,13 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
             const int n0 = __shfl_sync(act, n_int, 0);
             if (__all_sync(act, n_int == n0) && n0 >= 1 && n0 <= 3) n_uniform = (float)n0;
         }
-        *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)row * 16) = c;
+        *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
         if (row == 0) {
             float4 f;
             f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
             f.y = n_uniform;
             f.z = f.w = 0.0f;
-            *reinterpret_cast<float4*>(img + (size_t)3 * b_plane + (size_t)tc::TN * 16) = f;
+            *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
         }
     }
 }

@@ -64,9 +64,12 @@ int main(int argc, char** argv) {
     uint8_t* Pp = P.data() + ((16 - (uintptr_t)P.data() % 16) % 16);
     shim::launch3(tc_wimg_kernel, Dim3{(unsigned)Kpad / 16, (unsigned)n_dt, 1}, 128, (int64_t)0, (int)J, Kpad, omega.data(), a.data(),
                   b.data(), &dc, &td, G, delays.data(), n_dt, a_bytes, a_plane, Wp);
+    std::vector<PhiTabEntry> phitab(kPhiTabSize);
+    shim::launch(tc_phitab_kernel, kPhiTabSize / 256, 256, phitab.data());
     if (n_bt > 0)
         shim::launch3(tc_pimg_kernel, Dim3{(unsigned)n_bt, 1, 1}, 256, (int64_t)0, (int)J, Kpad, T, time.data(), expo.data(),
-                      counts.data(), perm.data(), flags, omega.data(), &dc, &td, n_bt, b_bytes, b_plane, Pp);
+                      counts.data(), perm.data(), flags, omega.data(), &dc, &td, (const PhiTabEntry*)phitab.data(), n_bt, b_bytes,
+                      b_plane, Pp);
 
     FILE* g = std::fopen(argv[3], "wb");
     if (!g) return 2;

@@ -79,7 +79,13 @@ struct Stat {
 static int run_funcs() {
     std::mt19937_64 rng(20261020);
     auto unif = [&](double lo, double hi) { return lo + (hi - lo) * ((double)(rng() >> 11) * (1.0 / 9007199254740992.0)); };
-    Stat e_poly, e_hilo, e_sin, e_cos, e_sin_df, e_cos_df, e_log_b0, e_log_b1, e_tiny;
+    Stat e_poly, e_hilo, e_sin, e_cos, e_sin_df, e_cos_df, e_sin_q30, e_cos_q30, e_log_b0, e_log_b1, e_tiny;
+    std::vector<PhiTabEntry> phitab(kPhiTabSize);
+    for (int k = 0; k < kPhiTabSize; ++k) {
+        const double ang = 6.283185307179586476925 * (double)k / (double)kPhiTabSize;
+        phitab[k].s = (int)std::llrint(std::sin(ang) * 1073741824.0);
+        phitab[k].c = (int)std::llrint(std::cos(ang) * 1073741824.0);
+    }
     const int N = 2000000;
     for (int i = 0; i < N; ++i) {
         const float x = (float)unif(-30.0, 30.0);
@@ -102,6 +108,11 @@ static int run_funcs() {
         if (sincos_phase_df(wh, wl, th, tl, s, c)) {
             e_sin_df.add((double)s - std::sin(w * t));
             e_cos_df.add((double)c - std::cos(w * t));
+        }
+        int qs, qc;  // the 2^-30 fixed-point route of the Phi image (table + first-order rotation)
+        if (sincos_phase_q30(wh, wl, th, tl, phitab.data(), qs, qc)) {
+            e_sin_q30.add((double)qs / 1073741824.0 - std::sin(w * t));
+            e_cos_q30.add((double)qc / 1073741824.0 - std::cos(w * t));
         }
     }
     // log2(1 + u) reconstruction y0 + lo/nl: independent of the seed error
@@ -130,6 +141,8 @@ static int run_funcs() {
     e_cos.print("cos_phase_abs");
     e_sin_df.print("sin_phase_df_abs");
     e_cos_df.print("cos_phase_df_abs");
+    e_sin_q30.print("sin_phase_q30_abs");
+    e_cos_q30.print("cos_phase_q30_abs");
     e_log_b0.print("log2_1pu_abs_mufu_like");
     e_log_b1.print("log2_1pu_abs_bad_seed");
     e_tiny.print("log2_1pu_tiny_rel", true);
@@ -205,9 +218,10 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     const float sigma_f = (float)std::ldexp(1.0, e), ks = (float)std::ldexp(1.0, -12 - e);
     const double ysc = std::isfinite(cabs) ? std::fmax(1.0, (double)dc.c_hi) : 1.0;
     const double crit = ysc * ysc * sumsq;
-    const int auto_mode = crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0);
-    // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run and no exponent can leave [-120, 120]
+    // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run; a draw whose exponent could leave [-120, 120]
+    // is evaluated by the fp64 epilogue whatever the option says (the fp32 epilogues evaluate 2^x without clamps)
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
+    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0));
     const int prod_mode = (auto_mode == 0 && xmax <= 120.0) ? 3 : auto_mode;
 
     // tc_perm_kernel: bins with counts first (stable); tc_perm_sorted_kernel (product epilogue): by count class 1, 2, 3, >= 4, 0
@@ -225,9 +239,16 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     for (int64_t i = 0; i < T; ++i)
         if (!(counts[i] > 0)) perm.push_back((int)i);
 
-    // tc_pimg_kernel: Phi digit planes [3][Tpad][Kpad] and per-bin constants
+    // tc_phitab_kernel: the 1024-point unit circle in 2^-30 fixed point
+    std::vector<PhiTabEntry> phitab(kPhiTabSize);
+    for (int k = 0; k < kPhiTabSize; ++k) {
+        const double ang = 6.283185307179586476925 * (double)k / (double)kPhiTabSize;
+        phitab[k].s = (int)std::llrint(std::sin(ang) * 1073741824.0);
+        phitab[k].c = (int)std::llrint(std::cos(ang) * 1073741824.0);
+    }
+    // tc_pimg_kernel: Phi digit planes [4][Tpad][Kpad] (2^-30 fixed point) and per-bin constants
     const int64_t Tpad = (int64_t)n_bt * cfg::TN;
-    std::vector<int8_t> P((size_t)3 * Tpad * Kpad, 0);
+    std::vector<int8_t> P((size_t)4 * Tpad * Kpad, 0);
     std::vector<float4> cst(Tpad);
     std::vector<float> wh(J), wl(J);
     for (int j = 0; j < J; ++j) {
@@ -246,23 +267,21 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
             int q0 = 0, q1 = 0;
             if (valid) {
                 if (k < 2 * J) {
-                    float sn, cn;
-                    if (exact_phi) {  // experiment (IPN_EMU_EXACT_PHI): float64 sin / cos, isolates the polynomials' share
-                        sn = (float)std::sin(omega[k >> 1] * t);
-                        cn = (float)std::cos(omega[k >> 1] * t);
-                    } else if (!sincos_phase_df(wh[k >> 1], wl[k >> 1], th, tl, sn, cn)) {
-                        sincos_phase(omega[k >> 1] * t, sn, cn);
+                    if (exact_phi) {  // experiment (IPN_EMU_EXACT_PHI): float64 sin / cos, isolates the fixed-point route's share
+                        q1 = (int)std::llrint(std::sin(omega[k >> 1] * t) * 1073741824.0);
+                        q0 = (int)std::llrint(std::cos(omega[k >> 1] * t) * 1073741824.0);
+                    } else if (!sincos_phase_q30(wh[k >> 1], wl[k >> 1], th, tl, phitab.data(), q1, q0)) {
+                        q1 = (int)std::llrint(std::sin(omega[k >> 1] * t) * 1073741824.0);
+                        q0 = (int)std::llrint(std::cos(omega[k >> 1] * t) * 1073741824.0);
                     }
-                    q0 = __float2int_rn(cn * 4194304.0f);
-                    q1 = __float2int_rn(sn * 4194304.0f);
                 } else {
-                    q0 = q1 = 4194304;
+                    q0 = q1 = 1073741824;
                 }
             }
-            int8_t dummy, d0[3], d1[3];
-            split_digits4(q0, dummy, d0[0], d0[1], d0[2]);
-            split_digits4(q1, dummy, d1[0], d1[1], d1[2]);
-            for (int pl = 0; pl < 3; ++pl) {
+            int8_t d0[4], d1[4];
+            split_digits4(q0, d0[0], d0[1], d0[2], d0[3]);
+            split_digits4(q1, d1[0], d1[1], d1[2], d1[3]);
+            for (int pl = 0; pl < 4; ++pl) {
                 P[((size_t)pl * Tpad + pos) * Kpad + k] = d0[pl];
                 P[((size_t)pl * Tpad + pos) * Kpad + k + 1] = d1[pl];
             }
@@ -323,7 +342,7 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
         // to be compared with what the kernels themselves produce (tests/emu/images_emu.cpp)
         const int TM = 128, n_dt = (int)((G + TM - 1) / TM);
         const size_t a_plane = (size_t)Kpad * TM, b_plane = (size_t)Kpad * cfg::TN;
-        const size_t a_bytes = 4 * a_plane, b_bytes = 3 * b_plane + cfg::TN * 16 + 16;
+        const size_t a_bytes = 4 * a_plane, b_bytes = 4 * b_plane + cfg::TN * 16 + 16;
         std::vector<uint8_t> Wi((size_t)n_dt * a_bytes, 0), Pi((size_t)n_bt * b_bytes, 0);
         for (int64_t g = 0; g < (int64_t)n_dt * TM; ++g) {
             w_digits(g, W);
@@ -334,13 +353,13 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
         for (int64_t pos = 0; pos < Tpad; ++pos) {
             uint8_t* img = &Pi[(size_t)(pos / cfg::TN) * b_bytes];
             const int row = (int)(pos % cfg::TN);
-            for (int pl = 0; pl < 3; ++pl)
+            for (int pl = 0; pl < 4; ++pl)
                 for (int k = 0; k < Kpad; ++k)
                     img[pl * b_plane + ((size_t)(k / 16) * cfg::TN + row) * 16 + k % 16] = (uint8_t)P[((size_t)pl * Tpad + pos) * Kpad + k];
-            std::memcpy(img + 3 * b_plane + (size_t)row * 16, &cst[pos], 16);
+            std::memcpy(img + 4 * b_plane + (size_t)row * 16, &cst[pos], 16);
             if (row == 0) {
                 const float4 fl = {(pos < n_nz) ? 1.0f : 0.0f, (float)n_uniform[pos / cfg::TN], 0.0f, 0.0f};
-                std::memcpy(img + 3 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
+                std::memcpy(img + 4 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
             }
         }
         FILE* g = std::fopen(dump_path, "wb");
@@ -372,19 +391,20 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const bool has_counts = (int64_t)bt * cfg::TN < n_nz;
-                // the nine digit-plane products of the tile (int32, exact), loglik_tc.cu header
+                // the ten digit-plane products of the tile (int32, exact), loglik_tc.cu header
                 for (int r = 0; r < cfg::TN; ++r) {
                     const size_t pos = (size_t)bt * cfg::TN + r;
                     const int8_t* p1 = &P[((size_t)0 * Tpad + pos) * Kpad];
                     const int8_t* p2 = &P[((size_t)1 * Tpad + pos) * Kpad];
                     const int8_t* p3 = &P[((size_t)2 * Tpad + pos) * Kpad];
+                    const int8_t* p4 = &P[((size_t)3 * Tpad + pos) * Kpad];
                     const int8_t *w1 = &W[0], *w2 = &W[Kpad], *w3 = &W[2 * Kpad], *w4 = &W[3 * Kpad];
                     int s2 = 0, s3 = 0, s4 = 0, s5 = 0;
                     for (int k = 0; k < Kpad; ++k) {
                         s2 += w1[k] * p1[k];
                         s3 += w2[k] * p1[k] + w1[k] * p2[k];
                         s4 += w3[k] * p1[k] + w2[k] * p2[k] + w1[k] * p3[k];
-                        s5 += w4[k] * p1[k] + w3[k] * p2[k] + w2[k] * p3[k];
+                        s5 += w4[k] * p1[k] + w3[k] * p2[k] + w2[k] * p3[k] + w1[k] * p4[k];
                     }
                     S2[r] = s2;
                     S3[r] = s3;
