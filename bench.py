@@ -351,8 +351,8 @@ def main():
                       "peak_fma_loop_measured": fma_measured, "frac_of_measured_fma_loop": fp32_equiv / fma_measured if fp32_equiv else None,
                       "peak_source": f"{sms} SM x 128 lanes x 2 x {sm_max:.0f} MHz; fma loop measured in this run"}}
         if impl == 2:
-            # tcgen05 back-end: 9 int8 digit-plane products x 224 K rows = 2016 MAC = 4032 int8 op per unit
-            ops = units_timed * 4032.0 / main_s / 1e12 if main_ms > 0 else None
+            # tcgen05 back-end: 12 int8 digit-plane products x 224 K rows = 2688 MAC = 5376 int8 op per unit
+            ops = units_timed * 5376.0 / main_s / 1e12 if main_ms > 0 else None
             # denominators: (i) the int8 tensor pipe as this kernel's MMA shape can drive it, MEASURED in this process right
             # after the timed region (ipn_microbench 2: back-to-back tcgen05.mma kind::i8 M128 N32 K32, A in tensor memory, on
             # every SM, timed with CUDA events -> at the clock the chip holds under that load); (ii) 2 x the bf16 figures
@@ -367,7 +367,7 @@ def main():
                     "frac_of_2x_bf16_burst": ops / (2.0 * bf16_burst) if ops and bf16_burst else None,
                     "peaks_file": {"bf16_tflops": bf16_burst, "bf16_tflops_sustained": bf16_sust,
                                    "note": "MEASURED_PEAKS.json (driver-written)" if peaks else "MEASURED_PEAKS.json absent"},
-                    "algorithmic_op_per_unit": 4032.0}
+                    "algorithmic_op_per_unit": 5376.0}
         else:
             roof = {"bound": "fp32", "achieved": fp32_equiv, "peak": fp32_nominal, "unit": "TFLOP/s",
                     "frac": fp32_equiv / fp32_nominal if fp32_equiv else None,

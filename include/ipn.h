@@ -111,6 +111,11 @@ int ipn_loglik_sky_grid(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t T
                         const double* exposure, const int64_t* counts, const double* sc_pos, int64_t P,
                         const double* ghat, int64_t S, int64_t J, const double* omega, const double* a,
                         const double* b, const double* amp, const double* bkg, double* ll);
+/* the same on device-resident arrays (only nbins, D small integers, stays a host array); d_ll (P x S) is overwritten */
+int ipn_loglik_sky_grid_dev(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t Tmax, const double* d_time,
+                            const double* d_exposure, const int64_t* d_counts, const double* d_sc_pos, int64_t P,
+                            const double* d_ghat, int64_t S, int64_t J, const double* d_omega, const double* d_a,
+                            const double* d_b, const double* d_amp, const double* d_bkg, double* d_ll);
 
 /* ---- posterior-predictive counts: drop-in for ppc_generator ------------------------------------------
  * replaces  pyipn/fit.py:694-705:  out[s*T + i] ~ Poisson((rates[s*T+i] + bkg[s]) * exposure[i]).

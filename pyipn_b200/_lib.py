@@ -33,7 +33,7 @@ EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_use_own_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
     "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_ctx_last_draw_batch", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
-    "ipn_loglik_sky_grid", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench", "ipn_sky_credible", "ipn_sky_credible_dev",
+    "ipn_loglik_sky_grid", "ipn_loglik_sky_grid_dev", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench", "ipn_sky_credible", "ipn_sky_credible_dev",
 )
 
 
@@ -88,6 +88,7 @@ def load_library(path: str | None = None):
         lib.ipn_loglik_delay_grid.argtypes = grid_args
         lib.ipn_loglik_delay_grid_dev.argtypes = grid_args
         lib.ipn_loglik_sky_grid.argtypes = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]
+        lib.ipn_loglik_sky_grid_dev.argtypes = lib.ipn_loglik_sky_grid.argtypes
         pc_args = [_p, _i64, _p, _i64, _p, _p, C.c_uint64, _p]
         lib.ipn_poisson_counts.argtypes = pc_args
         lib.ipn_poisson_counts_dev.argtypes = pc_args
@@ -255,6 +256,15 @@ class Context:
             self._h, D, _ptr(nbins), Tmax, _ptr(time), _ptr(exposure), _ptr(counts), _ptr(sc_pos), P, _ptr(ghat), S, J,
             _ptr(omega), _ptr(a), _ptr(b), _ptr(amp), _ptr(bkg), _ptr(out)))
         return out
+
+    def loglik_sky_grid_dev(self, nbins, Tmax, d_time, d_exposure, d_counts, d_sc_pos, P, d_ghat, S, J, d_omega, d_a, d_b, d_amp,
+                            d_bkg, d_ll):
+        """``loglik_sky_grid`` on device-resident arrays given as raw device pointers (ints); ``nbins`` is a host sequence of
+        the D per-detector bin counts.  Asynchronous on the context's stream; ``d_ll`` (P x S float64) is overwritten."""
+        nbins = np.ascontiguousarray(nbins, dtype=np.int64)
+        _check(self._lib, self._lib.ipn_loglik_sky_grid_dev(
+            self._h, int(nbins.size), _ptr(nbins), int(Tmax), _p(d_time), _p(d_exposure), _p(d_counts), _p(d_sc_pos), int(P),
+            _p(d_ghat), int(S), int(J), _p(d_omega), _p(d_a), _p(d_b), _p(d_amp), _p(d_bkg), _p(d_ll)))
 
     def thinning_events(self, tstart, tstop, K=(), t_start=(), t_rise=(), t_decay=(), bkg_slope=0.0, bkg_intercept=0.0,
                         seed=1234):

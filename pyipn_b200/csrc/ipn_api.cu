@@ -421,6 +421,29 @@ int ipn_loglik_delay_grid(ipn_ctx* ctx, int64_t T, const double* time, const dou
     return IPN_OK;
 }
 
+// functions.stan:37-61 + 65-69 on device arrays: delays per (detector, direction), then one delay-grid pass per detector
+// accumulating into d_ll (P x S).  nbins is a HOST array.  The per-detector passes share the 1e-3 nat tolerance of the sum,
+// so the epilogue choice of every pass is made for a 1 / D share of it (ctx->n_terms).
+static int sky_grid_device(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t Tmax, const double* d_time,
+                           const double* d_exposure, const int64_t* d_counts, const double* d_sc_pos, int64_t P,
+                           const double* d_ghat, int64_t S, int64_t J, const double* d_omega, const double* d_a,
+                           const double* d_b, const double* d_amp, const double* d_bkg, double* d_ll) {
+    int rc;
+    if ((rc = ctx->io[11].ensure((size_t)D * P * 8))) return rc;
+    rc = launch_sky_delays(ctx, D, d_sc_pos, P, d_ghat, ctx->io[11].as<double>());
+    if (rc) return rc;
+    ctx->n_terms = (int)D;
+    for (int64_t d = 0; d < D; ++d) {
+        // detector 0 is unshifted (rff_omega_ipn.stan:144): its delay column is identically zero, so a 1-point
+        // grid would do; it is kept on the common path (its cost is 1/D of the call) to share one code path.
+        rc = run_loglik_grid(ctx, nbins[d], d_time + d * Tmax, d_exposure + d * Tmax, d_counts + d * Tmax, S, J, d_omega, d_a, d_b,
+                             d_amp + d * S, d_bkg + d * S, P, ctx->io[11].as<double>() + d * P, d_ll, d != 0);
+        if (rc) break;
+    }
+    ctx->n_terms = 1;
+    return rc;
+}
+
 int ipn_loglik_sky_grid(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t Tmax, const double* time,
                         const double* exposure, const int64_t* counts, const double* sc_pos, int64_t P,
                         const double* ghat, int64_t S, int64_t J, const double* omega, const double* a,
@@ -452,26 +475,38 @@ int ipn_loglik_sky_grid(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t T
     if ((rc = h2d(ctx, ctx->io[8], sc_pos, (size_t)D * 3 * 8))) return rc;
     if ((rc = h2d(ctx, ctx->io[10], ghat, (size_t)P * 3 * 8))) return rc;
     if ((rc = ctx->io[9].ensure((size_t)P * S * 8))) return rc;
-    if ((rc = ctx->io[11].ensure((size_t)D * P * 8))) return rc;
     begin_timing(ctx);
-    rc = launch_sky_delays(ctx, D, ctx->io[8].as<double>(), P, ctx->io[10].as<double>(), ctx->io[11].as<double>());
+    rc = sky_grid_device(ctx, D, nbins, Tmax, ctx->io[0].as<double>(), ctx->io[1].as<double>(), ctx->io[2].as<int64_t>(),
+                         ctx->io[8].as<double>(), P, ctx->io[10].as<double>(), S, J, ctx->io[3].as<double>(), ctx->io[4].as<double>(),
+                         ctx->io[5].as<double>(), ctx->io[6].as<double>(), ctx->io[7].as<double>(), ctx->io[9].as<double>());
     if (rc) return rc;
-    bool first = true;
-    for (int64_t d = 0; d < D; ++d) {
-        // detector 0 is unshifted (rff_omega_ipn.stan:144): its delay column is identically zero, so a 1-point
-        // grid would do; it is kept on the common path (its cost is 1/D of the call) to share one code path.
-        rc = run_loglik_grid(ctx, nbins[d], ctx->io[0].as<double>() + d * Tmax, ctx->io[1].as<double>() + d * Tmax,
-                             ctx->io[2].as<int64_t>() + d * Tmax, S, J, ctx->io[3].as<double>(), ctx->io[4].as<double>(),
-                             ctx->io[5].as<double>(), ctx->io[6].as<double>() + d * S, ctx->io[7].as<double>() + d * S, P,
-                             ctx->io[11].as<double>() + d * P, ctx->io[9].as<double>(), !first);
-        if (rc) return rc;
-        first = false;
-    }
     end_timing(ctx);
     IPN_CUDA_CHECK(cudaMemcpyAsync(ll, ctx->io[9].p, (size_t)P * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
     IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     finish_timing(ctx);
     return IPN_OK;
+}
+
+int ipn_loglik_sky_grid_dev(ipn_ctx* ctx, int64_t D, const int64_t* nbins, int64_t Tmax, const double* d_time,
+                            const double* d_exposure, const int64_t* d_counts, const double* d_sc_pos, int64_t P,
+                            const double* d_ghat, int64_t S, int64_t J, const double* d_omega, const double* d_a,
+                            const double* d_b, const double* d_amp, const double* d_bkg, double* d_ll) {
+    int rc = ctx_guard(ctx);
+    if (rc) return rc;
+    IPN_REQUIRE(D >= 1 && Tmax >= 0, "need D >= 1 and Tmax >= 0");
+    rc = check_grid_shapes(Tmax, S, J, P);
+    if (rc) return rc;
+    if (S == 0 || P == 0) return IPN_OK;
+    IPN_REQUIRE(nbins && d_sc_pos && d_ghat && d_omega && d_a && d_b && d_amp && d_bkg && d_ll &&
+                    (Tmax == 0 || (d_time && d_exposure && d_counts)),
+                "NULL array argument");
+    for (int64_t d = 0; d < D; ++d)
+        IPN_REQUIRE(nbins[d] >= 0 && nbins[d] <= Tmax, "nbins[%lld] = %lld outside 0..Tmax", (long long)d, (long long)nbins[d]);
+    begin_timing(ctx);
+    rc = sky_grid_device(ctx, D, nbins, Tmax, d_time, d_exposure, d_counts, d_sc_pos, P, d_ghat, S, J, d_omega, d_a, d_b, d_amp,
+                         d_bkg, d_ll);
+    end_timing(ctx);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -21,6 +21,18 @@ __device__ __forceinline__ void split_digits4(int q, int8_t& d1, int8_t& d2, int
     d4 = (int8_t)e4;
 }
 
+// Five signed 8-bit digits of a 40-bit integer (W sigma 2^38): q = d1 2^32 + d2 2^24 + d3 2^16 + d4 2^8 + d5, d2..d5 in [-128, 127]
+__device__ __forceinline__ void split_digits5(long long q, int8_t& d1, int8_t& d2, int8_t& d3, int8_t& d4, int8_t& d5) {
+    const int e5 = (int)(((q + 128) & 255) - 128);
+    const long long r = (q - e5) >> 8;  // |r| <= 2^30 + 1
+    d5 = (int8_t)e5;
+    split_digits4((int)r, d1, d2, d3, d4);
+}
+
+// The level-6 sum (W's fifth digit times Phi's first, weight 2^-8 of level 5) rounded into level-5 units: what the epilogue
+// threads do with the fifth accumulator right after loading it (two integer instructions per bin)
+__device__ __forceinline__ int fold_level6(int s5, int s6) { return s5 + ((s6 + 128) >> 8); }
+
 // Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, compensated sum.
 // HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
 template <bool HC>
@@ -44,12 +56,30 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
             v[j] = -fmaf(c.y, u, c.z * u);
         }
     }
+#if !defined(IPN_EPI_KAHAN) || IPN_EPI_KAHAN == 8
     // pairwise sum of the eight terms (|partial| <= 8 |v|), then ONE Kahan step into the running sum
     const float g = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     const float yk = g - scomp;
     const float tt = ssum + yk;
     scomp = (tt - ssum) - yk;
     ssum = tt;
+#elif IPN_EPI_KAHAN == 2
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float yk = (v[j] + v[j + 1]) - scomp;
+        const float tt = ssum + yk;
+        scomp = (tt - ssum) - yk;
+        ssum = tt;
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float yk = v[j] - scomp;
+        const float tt = ssum + yk;
+        scomp = (tt - ssum) - yk;
+        ssum = tt;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------

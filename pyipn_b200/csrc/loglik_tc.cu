@@ -7,21 +7,28 @@
 // random ~1.4e-6 error in every exponent.  Integer tensor-core accumulation is EXACT, so the contraction can
 // be done to any precision by slicing the operands into signed 8-bit digits (an Ozaki-style splitting):
 //
-//   Phi (|.| <= 1)   = (p1 2^16 + p2 2^8 + p3) 2^-22                 3 digit planes  (|error| <= 2^-23, per bin)
-//   W sigma (|.|<=1) = (w1 2^24 + w2 2^16 + w3 2^8 + w4) 2^-30        4 digit planes  (sigma = power of two)
-//   x = sum_k Phi W  = kappa [ S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5 ],  kappa = 2^-12 / sigma
-//   S2 = w1.p1   S3 = w2.p1 + w1.p2   S4 = w3.p1 + w2.p2 + w1.p3   S5 = w4.p1 + w3.p2 + w2.p3     (9 int8 GEMMs)
-//
-// (digit products of total weight < 2^-40 are dropped: < 1e-8 in x).  The additive constant log2(A/B) of the
+//   Phi (|.| <= 1)   = (p1 2^24 + p2 2^16 + p3 2^8 + p4) 2^-30                 4 digit planes  (|error| <= 2^-31, per bin)
+//   W sigma (|.|<=1) = (w1 2^32 + w2 2^24 + w3 2^16 + w4 2^8 + w5) 2^-38        5 digit planes  (sigma = power of two)
+//   x = sum_k Phi W  = kappa [ S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5 + 2^-32 S6 ],  kappa = 2^-12 / sigma
+//   S2 = w1.p1   S3 = w2.p1 + w1.p2   S4 = w3.p1 + w2.p2 + w1.p3   S5 = w4.p1 + w3.p2 + w2.p3 + w1.p4   S6 = w5.p1 + w4.p2
+//                                                                                                  (12 int8 GEMMs)
+// Which products are kept follows from how their errors add up over the bins.  A rounding error of Phi is random from bin
+// to bin, so it enters a sum over 1e5 bins with sqrt(sum r_i^2) (r_i = d ll / d x_i, the Poisson residual weight); a
+// rounding error of W -- and every dropped product of a fixed W digit with a SMOOTH Phi digit (p1, p2) -- is the same for
+// all bins of a (delay, draw), so it enters with the coherent sum_i r_i Phi_ik, which for a model that is off by 1e4 nats
+// (every posterior draw but the best few) is 100 times larger.  Measured on the bench draws before the fifth W digit and
+// the w4.p2 product existed: up to 1.6e-3 nats.  The level-6 products with the pseudo-random low Phi digits (w3.p3, w2.p4)
+// and everything below are dropped (< 1e-8 in x, random).  The additive constant log2(A/B) of the
 // draw rides along as extra K rows (Phi = 1, W = c sigma / n_rows), so x comes out of the tensor core complete.
 //
-// Mapping: MMA M = 128 trial delays, N = 32 time bins, K = 32 per UTCIMMA.  The W digits of a work item
-// (draw, 128 delays) are staged once through shared memory into TENSOR MEMORY (tcgen05.cp, 224 columns) and
-// used as the A operand from there: with both operands in shared memory the 63 MMAs of a tile would re-read
+// Mapping: MMA M = 128 trial delays, N = 32 time bins, K = 32 per UTCIMMA.  The first four W digits of a work item
+// (draw, 128 delays) are staged once through shared memory into TENSOR MEMORY (tcgen05.cp, 224 columns, two planes at a
+// time) and used as the A operand from there; the fifth digit plane stays in shared memory for the item (one product, SS
+// form).  Why tensor memory: with both operands in shared memory the 63 MMAs of a tile would re-read
 // the 128-row A operand every time (6 KB per 32-cycle MMA = 192 B/clk, more than shared memory delivers; measured
 // ~75 cycles per MMA).  The Phi digits (B operand, 21 KB per tile) stream through a 4-stage bulk-copy ring, the
 // tiles' Poisson constants through a separate 6-deep ring.  4 level accumulators x 32 columns x 2 buffers sit in
-// TMEM columns [256, 512).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
+// TMEM columns [256, 512), the level-6 accumulator single-buffered in the 32 columns left, [224, 256).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
 // bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
 // and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
 // Warp roles: 0..15 = epilogue, 16 = bulk-copy producer, 17 / 18 = MMA issuers of the even / odd tiles (17 also does the
@@ -79,7 +86,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Where a timed-out wait leaves its identity before trapping (host-mapped, see trap_record_device_ptr()).
 __device__ int* g_trap_record = nullptr;
-enum WaitId { W_A_FULL = 1, W_A_EMPTY, W_A_TMEM_FULL, W_A_TMEM_FREE, W_B_FULL, W_B_EMPTY, W_C_FULL, W_C_EMPTY, W_T_FULL, W_T_EMPTY };
+enum WaitId { W_A_FULL = 1, W_A_EMPTY, W_A_TMEM_FULL, W_A_TMEM_FREE, W_B_FULL, W_B_EMPTY, W_C_FULL, W_C_EMPTY, W_T_FULL, W_T_EMPTY, W_W5_FULL, W_T6_EMPTY };
 
 __device__ __noinline__ void mbar_timeout(int id, uint32_t parity, uint32_t seq, const volatile uint32_t* prog) {
     int* r = g_trap_record;
@@ -247,12 +254,14 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // (every role skips the others' items), so the common fp32 instantiation carries no compensated or fp64 code in its
 // instruction-cache footprint.
 enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, EPI_PROD = 3 };
+// (register budget: 96 per thread -- 19 warps x 32 x 104 does not launch, the allocation granule is 512 registers per warp)
 template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;                                               // staging of the W digit planes
-    uint8_t* sB0 = smem + p.a_bytes;                                  // [NBST][b_dig]  Phi digit planes
+    uint8_t* sW5 = smem;                                              // fifth W digit plane of the current item (resident)
+    uint8_t* sA = smem + p.a_plane;                                   // staging of W digit planes 1-4, two at a time
+    uint8_t* sB0 = sA + 2 * (size_t)p.a_plane;                        // [NBST][b_dig]  Phi digit planes
     uint8_t* sC0 = sB0 + NBST * (size_t)p.b_dig;                      // [NCST][CONST_BYTES]  Poisson constants
     uint64_t* bars = reinterpret_cast<uint64_t*>(sC0 + NCST * CONST_BYTES);
     uint64_t* a_full = bars + 0;
@@ -264,8 +273,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* c_full = b_empty + NBST;       // [NCST]
     uint64_t* c_empty = c_full + NCST;       // [NCST]
     uint64_t* a_tmem_full = c_empty + NCST;  // W digits of the current item are in tensor memory (issuer 0 -> issuer 1)
-    uint64_t* a_tmem_free = a_tmem_full + 1; // both issuers' MMAs of the item have finished reading them (-> issuer 0)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_tmem_free + 1);
+    uint64_t* a_tmem_free = a_tmem_full + 1; // both issuers' MMAs of the item have finished reading them (-> issuer 0, producer)
+    uint64_t* w5_full = a_tmem_free + 1;     // fifth W digit plane of the item is in shared memory (-> both issuers)
+    uint64_t* t6_empty = w5_full + 1;        // [2] level-6 accumulator drained by the epilogue of tile n - 1 (-> issuer of tile n, n % 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t6_empty + 2);
     volatile uint32_t* prog = tmem_slot + 4;  // [24] last wait of every warp (time-out diagnostics)
     static_assert(NTHREADS / 32 <= 24, "prog[] holds one word per warp");
 
@@ -279,6 +290,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         mbar_init(a_empty, 1);
         mbar_init(a_tmem_full, 1);
         mbar_init(a_tmem_free, 2);
+        mbar_init(w5_full, 1);
+        mbar_init(t6_empty + 0, EPI_ARRIVALS);
+        mbar_init(t6_empty + 1, EPI_ARRIVALS);
         for (int i = 0; i < NBUF; ++i) mbar_init(t_empty + i, EPI_ARRIVALS);
         for (int i = 0; i < NTF; ++i) mbar_init(t_full + i, 1);
         for (int i = 0; i < NBFULL; ++i) mbar_init(b_full + i, 1);
@@ -316,9 +330,18 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 }
                 const int rem = (int)(item - (int64_t)sl * items_per_draw);
                 const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
-                mbar_wait_relaxed(a_empty, (item_seq & 1) ^ 1, W_A_EMPTY, item_seq, prog);  // staging buffer copied into TMEM
-                mbar_expect_tx(a_full, p.a_bytes);
-                bulk_g2s(sA, p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes, p.a_bytes, a_full);
+                // W digit planes 1-4 through the staging buffer, two planes at a time (a_full / a_empty change phase twice per
+                // item); plane 5 into its resident buffer once every MMA of the previous item has completed
+                const uint8_t* wimg = p.Wimg + ((int64_t)sl * p.n_dt + dt) * p.a_bytes;
+                mbar_wait_relaxed(a_empty, 1, W_A_EMPTY, item_seq, prog);  // second half of the previous item copied into TMEM
+                mbar_expect_tx(a_full, 2 * p.a_plane);
+                bulk_g2s(sA, wimg, 2 * p.a_plane, a_full);
+                mbar_wait_relaxed(a_tmem_free, (item_seq & 1) ^ 1, W_A_TMEM_FREE, item_seq, prog);
+                mbar_expect_tx(w5_full, p.a_plane);
+                bulk_g2s(sW5, wimg + 4 * (size_t)p.a_plane, p.a_plane, w5_full);
+                mbar_wait_relaxed(a_empty, 0, W_A_EMPTY, item_seq, prog);  // first half of this item copied into TMEM
+                mbar_expect_tx(a_full, 2 * p.a_plane);
+                bulk_g2s(sA, wimg + 2 * (size_t)p.a_plane, 2 * p.a_plane, a_full);
                 const int bt0 = chunk * p.tiles_per_chunk;
                 const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
                 for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
@@ -350,6 +373,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         // descriptor template: LBO / SBO / version bits; the 14-bit start-address field is added per use
         const uint64_t a_tmpl = make_desc(0, a_lbo, 128), b_tmpl = make_desc(0, b_lbo, 128);
         const uint32_t a_base = smem_u32(sA) >> 4;
+        const uint32_t w5_base = smem_u32(sW5) >> 4;
         const uint32_t b_base0 = smem_u32(sB0) >> 4;
         uint32_t tile_seq = 0, item_seq = 0;
         unsigned long long w_af = 0, w_bf = 0, w_te = 0;
@@ -365,27 +389,31 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const int bt0 = chunk * p.tiles_per_chunk;
             const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
             if (which == 0) {
-                mbar_wait_timed(a_full, item_seq & 1, w_af, dbg, W_A_FULL, item_seq, prog);
-                mbar_wait(a_tmem_free, (item_seq & 1) ^ 1, W_A_TMEM_FREE, item_seq, prog);  // all MMAs of the previous item have read its W digits
-                tc_fence_after();
-                if (elect_one()) {
-                    // W digit planes: shared -> tensor memory, 8 columns (32 K-bytes x 128 lanes) per copy.  PTX orders
-                    // cp -> mma of one thread but not mma -> cp, hence the a_tmem_free hand-shake above (a pipeline drain
-                    // per item, i.e. per >= 16 tiles).
+                // W digit planes 1-4: shared -> tensor memory, 8 columns (32 K-bytes x 128 lanes) per copy, two planes per
+                // staging-buffer fill.  PTX orders cp -> mma of one thread but not mma -> cp, hence the a_tmem_free hand-shake
+                // (a pipeline drain per item, i.e. per >= 16 tiles).
 #pragma unroll
-                    for (int q = 0; q < PW; ++q)
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait_timed(a_full, half, w_af, dbg, W_A_FULL, item_seq, prog);
+                    if (half == 0) mbar_wait(a_tmem_free, (item_seq & 1) ^ 1, W_A_TMEM_FREE, item_seq, prog);  // all MMAs of the previous item have read its W digits
+                    tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < KSTEPS; ++ks)
-                            tc_cp_128x256b(tmem_base + (q * KSTEPS + ks) * 8,
-                                           a_tmpl + (uint64_t)(a_base + q * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4)));
-                    tc_commit(a_empty);      // staging buffer free once the copies have completed
-                    tc_commit(a_tmem_full);  // ... and issuer 1 may start on this item
+                        for (int q = 2 * half; q < 2 * half + 2; ++q)
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+                                tc_cp_128x256b(tmem_base + (q * KSTEPS + ks) * 8,
+                                               a_tmpl + (uint64_t)(a_base + (q & 1) * (p.a_plane >> 4) + ks * (2 * a_lbo >> 4)));
+                        tc_commit(a_empty);                     // staging buffer free once the copies have completed
+                        if (half == 1) tc_commit(a_tmem_full);  // ... and issuer 1 may start on this item
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             } else {
                 mbar_wait(a_tmem_full, item_seq & 1, W_A_TMEM_FULL, item_seq, prog);
                 tc_fence_after();
             }
+            mbar_wait(w5_full, item_seq & 1, W_W5_FULL, item_seq, prog);  // the fifth digit plane is in shared memory
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 if ((IPN_HOOK(one_issuer) ? 0u : (tile_seq & 1)) != which) continue;
                 const uint32_t st = tile_seq % NBST;
@@ -406,8 +434,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
 #pragma unroll
                             for (int lev = 0; lev < NLEV; ++lev) {
                                 const int q = lev - pp;
-                                if (q < 0 || q >= PW) continue;
-                                const bool first = (pp == 0) || (lev - (pp - 1) >= PW);  // first product of this level
+                                if (q < 0 || q >= PWT) continue;
+                                const bool first = (pp == 0) || (lev - (pp - 1) >= PWT);  // first product of this level
                                 const uint32_t at = tmem_base + (q * KSTEPS + ks) * 8;
                                 const uint64_t bd = b_tmpl + (uint64_t)(b_base + pp * (p.b_plane >> 4) + ks * (2 * b_lbo >> 4));
                                 if (first && ks == 0)
@@ -415,6 +443,38 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                                 else
                                     tc_mma_i8_ts<true>(d0 + lev * TN, at, bd, idesc);
                             }
+                        }
+                    }
+                }
+                __syncwarp();
+                // level 6 (w4.p2 from tensor memory, w5.p1 with both operands in shared memory) into the single-buffered
+                // accumulator: the epilogue of the PREVIOUS tile must have drained it.  t6_empty[n % 2] belongs to the issuer of
+                // the tiles n = this parity and completes one phase per tile n - 1, from tile 1 on.
+                if (tile_seq > 0) mbar_wait_timed(t6_empty + (tile_seq & 1), ((tile_seq - 1) >> 1) & 1, w_te, dbg, W_T6_EMPTY, tile_seq, prog);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d6 = tmem_base + L6_COL0;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        if (IPN_HOOK(skip_mma) && ks > 0) break;
+                        const uint64_t bd1 = b_tmpl + (uint64_t)(b_base + ks * (2 * b_lbo >> 4));
+#ifndef IPN_TC_L6
+#define IPN_TC_L6 2  // experiment switch: 2 = both level-6 products (default), 1 = w4.p2 only, 0 = w5.p1 only
+#endif
+                        if (IPN_TC_L6 != 0) {
+                            const uint64_t bd2 = bd1 + (uint64_t)(p.b_plane >> 4);
+                            if (ks == 0)
+                                tc_mma_i8_ts<false>(d6, tmem_base + (3 * KSTEPS + ks) * 8, bd2, idesc);
+                            else
+                                tc_mma_i8_ts<true>(d6, tmem_base + (3 * KSTEPS + ks) * 8, bd2, idesc);
+                        }
+                        if (IPN_TC_L6 == 2)
+                            tc_mma_i8<true>(d6, a_tmpl + (uint64_t)(w5_base + ks * (2 * a_lbo >> 4)), bd1, idesc);
+                        else if (IPN_TC_L6 == 0) {
+                            if (ks == 0)
+                                tc_mma_i8<false>(d6, a_tmpl + (uint64_t)(w5_base + ks * (2 * a_lbo >> 4)), bd1, idesc);
+                            else
+                                tc_mma_i8<true>(d6, a_tmpl + (uint64_t)(w5_base + ks * (2 * a_lbo >> 4)), bd1, idesc);
                         }
                     }
                     tc_commit(b_empty + st);  // operands of this stage consumed
@@ -474,10 +534,41 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
                     int acc[NH][NLEV][8];
+                    // Two rounds of tensor-memory loads so that no more than 64 accumulator registers are live at once.
+                    // First the lowest level and level 6 (weight 2^-8 of it, single-buffered): fold, and hand the level-6
+                    // columns back at once -- the issuer of the NEXT tile waits for them.
+                    {
+                        int acc6[GCOLS];
+                        if (NH == 2) {
+                            int v[16];
+                            tc_ld16(t0 + (NLEV - 1) * TN, v);
+                            tc_ld16(tmem_base + L6_COL0 + lane_addr + cg * GCOLS, reinterpret_cast<int(&)[16]>(acc6));
+                            tc_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                acc[0][NLEV - 1][j] = fold_level6(v[j], acc6[j]);
+                                acc[NH - 1][NLEV - 1][j] = fold_level6(v[8 + j], acc6[8 + j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < NH; ++h) {
+                                tc_ld8(t0 + (NLEV - 1) * TN + h * 8, acc[h][NLEV - 1]);
+                                tc_ld8(tmem_base + L6_COL0 + lane_addr + cg * GCOLS + h * 8, reinterpret_cast<int(&)[8]>(acc6[h * 8]));
+                            }
+                            tc_wait_ld();
+#pragma unroll
+                            for (int h = 0; h < NH; ++h)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[h][NLEV - 1][j] = fold_level6(acc[h][NLEV - 1][j], acc6[h * 8 + j]);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(t6_empty + ((tile_seq + 1) & 1));
+                    }
                     if (NH == 2) {
                         // one 16-column load per level instead of two 8-column ones
 #pragma unroll
-                        for (int lev = 0; lev < NLEV; ++lev) {
+                        for (int lev = 0; lev < NLEV - 1; ++lev) {
                             int v[16];
                             tc_ld16(t0 + lev * TN, v);
 #pragma unroll
@@ -490,7 +581,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
 #pragma unroll
                         for (int h = 0; h < NH; ++h)
 #pragma unroll
-                            for (int lev = 0; lev < NLEV; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
+                            for (int lev = 0; lev < NLEV - 1; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
                     }
                     tc_wait_ld();
                     // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
@@ -583,7 +674,8 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     const uint32_t a_plane = (uint32_t)Kpad * TM, b_plane = (uint32_t)Kpad * TN;
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
     if ((rc0 = ensure_phitab(ctx))) return rc0;
-    const size_t smem = (size_t)a_bytes + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (4 + NBUF + NTF + NBFULL + NBST + 2 * NCST) * 8 + 16 + 24 * 4;
+    // fifth W plane (resident) + two-plane staging buffer + Phi ring + constants ring + barriers + TMEM slot + wait log
+    const size_t smem = 3 * (size_t)a_plane + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (7 + NBUF + NTF + NBFULL + NBST + 2 * NCST) * 8 + 16 + 24 * 4;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;
@@ -646,7 +738,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
         IPN_CUDA_CHECK(cudaMemsetAsync(d_R, 0, (size_t)Sb * Gpad * sizeof(double), ctx->stream));
-        tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_nnz, d_td);
+        tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_nnz, ctx->n_terms, d_td);
         tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
                                                                             n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)

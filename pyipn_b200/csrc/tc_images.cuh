@@ -15,7 +15,8 @@ constexpr int TM = 128;       // delays per tile (MMA M, TMEM lanes)
 #endif
 constexpr int TN = IPN_TC_TN; // bins per tile (MMA N, TMEM columns per level)
 constexpr int NLEV = 4;       // level accumulators S2..S5
-constexpr int PW = 4;         // W digit planes
+constexpr int PW = 5;         // W digit planes (W sigma to 2^-39)
+constexpr int PWT = 4;        // ... of which the first four live in tensor memory; the fifth stays in shared memory (one product)
 #ifndef IPN_TC_PP
 #define IPN_TC_PP 4
 #endif
@@ -54,14 +55,16 @@ constexpr int OWN_PERIOD = EPI_SLOTS / cgcd(GROUPS, EPI_SLOTS);  // tiles after 
 constexpr int NCST = (6 % OWN_PERIOD == 0) ? 6 : 2 * OWN_PERIOD;  // depth of the shared-memory ring of those constant blocks
 constexpr int NTF = NCST;                  // "accumulators complete" barriers: tile % NTF
 static_assert(NCST % OWN_PERIOD == 0 && NTF % OWN_PERIOD == 0 && NTF % 2 == 0, "epilogue barriers must not be shared between owner sets");
-constexpr int NBST = (PP == 4 ? 96 : 128) / TN;  // depth of the Phi digit-plane ring (3 tiles of 32 bins x 4 planes, or 4 x 3 planes: 86 KB)
+constexpr int NBST = 128 / TN;             // depth of the Phi digit-plane ring (4 tiles of 32 bins x 4 planes: 112 KB)
 constexpr int NBUF = 256 / (NLEV * TN);    // accumulator buffers in TMEM columns [256, 512)
 constexpr int NBFULL = (NBST % 2 == 0) ? NBST : 2 * NBST;  // "stage filled" barriers: tile % NBFULL.  The two MMA issuers take
                                            // alternate tiles, and a parity wait is only sound if the waiter sees every phase of
                                            // its barrier: with an odd ring depth a stage alternates between the issuers, so the
                                            // barriers (not the stages) are doubled and each one belongs to one issuer
 static_assert(NBUF >= 2 && NBUF % 2 == 0 && NTF >= NBUF, "each accumulator buffer belongs to one issuer");
-constexpr int ACC_COL0 = 256;              // TMEM: W digits in columns [0, 224), accumulators in [256, 512)
+constexpr int ACC_COL0 = 256;              // TMEM: W digits 1-4 in columns [0, 224), level-6 accumulator in [224, 256), levels 2-5 x 2 buffers in [256, 512)
+constexpr int L6_COL0 = 224;               // the single-buffered level-6 accumulator (TN columns)
+static_assert(L6_COL0 + TN <= ACC_COL0 && PWT * (KPAD_MAX / 4) <= L6_COL0, "tensor-memory map");
 }  // namespace tc
 
 struct TcDraw {
@@ -81,7 +84,7 @@ struct TcDraw {
 // sigma / kappa of every draw: sigma = largest power of two with sigma*max|W| <= 1 and sigma*|c| <= n_crows
 __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const double* __restrict__ a,
                                const double* __restrict__ b, const DrawConst* __restrict__ dc, const int* __restrict__ flags,
-                               TcDraw* __restrict__ td) {
+                               int n_terms, TcDraw* __restrict__ td) {
     const int sl = blockIdx.x * blockDim.x + threadIdx.x;
     if (sl >= Sb) return;
     const int64_t s = S0 + sl;
@@ -99,15 +102,18 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     TcDraw t;
     t.sigma = (float)ldexp(1.0, e);
     t.ks = (float)ldexp(1.0, -12 - e);
-    // fp32 epilogue error model: rms |dll| ~ 3.5e-8 ln2 y sqrt(sum n_i^2) with y ~ max(1, log2(A/B)) the size of
-    // log2(1+u).  Above ~2.5e-5 nats rms predicted (bright, coarsely binned data, or a source far above the background) the
-    // draw is evaluated with the compensated fp32 epilogue, above ~2.5e-4 with the fp64 one.  flags[1] = IPN_OPT_HIFI:
-    // 0 auto, 1 always fp64, 2 always plain fp32, 3 always compensated fp32.
+    // fp32 epilogue error model: every bin's term n y - kappa u is rounded at its own size, so
+    // rms |dll| ~ 1.5e-7 y sqrt(sum n_i^2) with y the typical log2(1 + u) of the bins that hold the counts -- 2-3 for a burst
+    // standing a few times above the background, more when A >> B (measured on the bench data, sum n^2 = 4.5e5: 1.2e-4 rms,
+    // 4.4e-4 max; compensated fp32: 8e-5 / 4.6e-4, dominated by other terms).  The draw goes to the compensated fp32
+    // epilogue when that prediction, times the n_terms detector passes a sky-grid call adds up, exceeds ~1.5e-4 nats, and to
+    // the fp64 epilogue above ~1.5e-3 (bright, coarsely binned data).  flags[1] = IPN_OPT_HIFI: 0 auto, 1 always fp64, 2
+    // always plain fp32, 3 always compensated fp32.
     const double sumsq = *reinterpret_cast<const double*>(flags + 2);
     const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
     // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
-    const double crit = ysc * ysc * sumsq;
-    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0))));
+    const double crit = ysc * ysc * sumsq * (double)(n_terms > 1 ? n_terms : 1);
+    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0))));
     // flags[1] = 4 (opt-in, IPN_OPT_HIFI = 4): the product epilogue (EPI_PROD, loglik_epilogue.cuh) for the draws the plain
     // fp32 epilogue would get, provided no exponent can leave [-120, 120] (|x| <= |c| + log2e sum_j |(a_j, b_j)|, the phases
     // of all frequencies aligned; ~40 for a draw of the prior): that epilogue evaluates 2^x without clamps.  The other
@@ -136,11 +142,11 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
     const double sigma = (double)td[sl].sigma;
     const double cs = (double)dc[s].c_hi + (double)dc[s].c_lo;
     const int ncrow = Kpad - 2 * J;
-    alignas(16) int8_t d[4][16];
+    alignas(16) int8_t d[tc::PW][16];
     const double dl = (g < G) ? delays[g] : 0.0;
     for (int kk = 0; kk < 16; kk += 2) {
         const int k = kc * 16 + kk;
-        int q0 = 0, q1 = 0;
+        long long q0 = 0, q1 = 0;
         if (g < G) {
             if (k < 2 * J) {
                 const int j = k >> 1;
@@ -148,24 +154,24 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
                 double sn, cn;
                 sincos(w * dl, &sn, &cn);
                 // saturate instead of wrapping if a caller of the _dev entry point passes amplitudes beyond the supported range
-                q0 = (int)llrint(fmin(fmax(kLog2e * (aj * cn - bj * sn) * sigma, -1.0), 1.0) * 1073741824.0);
-                q1 = (int)llrint(fmin(fmax(kLog2e * (aj * sn + bj * cn) * sigma, -1.0), 1.0) * 1073741824.0);
+                q0 = llrint(fmin(fmax(kLog2e * (aj * cn - bj * sn) * sigma, -1.0), 1.0) * 274877906944.0);  // 2^38
+                q1 = llrint(fmin(fmax(kLog2e * (aj * sn + bj * cn) * sigma, -1.0), 1.0) * 274877906944.0);
             } else if (isfinite(cs)) {
                 // additive constant c spread exactly over the ncrow constant rows
-                const long long tot = llrint(cs * sigma * 1073741824.0);
+                const long long tot = llrint(cs * sigma * 274877906944.0);
                 const long long base = tot / ncrow, rem = tot - base * ncrow;  // |rem| < ncrow, same sign as tot
                 const int i0 = k - 2 * J, i1 = i0 + 1;
                 const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
-                q0 = (int)(base + (i0 < ar ? sg : 0));
-                q1 = (int)(base + (i1 < ar ? sg : 0));
+                q0 = base + (i0 < ar ? sg : 0);
+                q1 = base + (i1 < ar ? sg : 0);
             }
         }
-        split_digits4(q0, d[0][kk], d[1][kk], d[2][kk], d[3][kk]);
-        split_digits4(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[3][kk + 1]);
+        split_digits5(q0, d[0][kk], d[1][kk], d[2][kk], d[3][kk], d[4][kk]);
+        split_digits5(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[3][kk + 1], d[4][kk + 1]);
     }
     uint8_t* img = Wimg + ((int64_t)sl * n_dt + dt) * a_bytes;
 #pragma unroll
-    for (int pl = 0; pl < 4; ++pl)
+    for (int pl = 0; pl < tc::PW; ++pl)
         *reinterpret_cast<int4*>(img + (size_t)pl * a_plane + ((size_t)kc * tc::TM + row) * 16) =
             *reinterpret_cast<const int4*>(d[pl]);
 }

@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
                      flags, hifi_mode);
     }
     TcDraw td;
-    shim::launch(tc_draw_kernel, 1, 128, (int64_t)0, 1, (int)J, Kpad - 2 * (int)J, a.data(), b.data(), &dc, flags, &td);
+    shim::launch(tc_draw_kernel, 1, 128, (int64_t)0, 1, (int)J, Kpad - 2 * (int)J, a.data(), b.data(), &dc, flags, 1, &td);
     std::vector<uint8_t> W((size_t)n_dt * a_bytes + 16, 0xAB), P((size_t)n_bt * b_bytes + 16, 0xAB);
     uint8_t* Wp = W.data() + ((16 - (uintptr_t)W.data() % 16) % 16);  // 16-byte aligned like device allocations
     uint8_t* Pp = P.data() + ((16 - (uintptr_t)P.data() % 16) % 16);

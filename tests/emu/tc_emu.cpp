@@ -221,7 +221,7 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run; a draw whose exponent could leave [-120, 120]
     // is evaluated by the fp64 epilogue whatever the option says (the fp32 epilogues evaluate 2^x without clamps)
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
-    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 1.0e6 ? 1 : 0));
+    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0));  // n_terms = 1
     const int prod_mode = (auto_mode == 0 && xmax <= 120.0) ? 3 : auto_mode;
 
     // tc_perm_kernel: bins with counts first (stable); tc_perm_sorted_kernel (product epilogue): by count class 1, 2, 3, >= 4, 0
@@ -258,6 +258,8 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     }
     const bool src = std::isfinite(dc.c_hi);
     const bool exact_phi = std::getenv("IPN_EMU_EXACT_PHI") != nullptr;
+    const bool no_w5 = std::getenv("IPN_EMU_NO_W5") != nullptr;  // experiment: drop the fifth W digit (W to 2^-31 only)
+    const bool no_p2w4 = std::getenv("IPN_EMU_NO_P2W4") != nullptr;
     for (int64_t pos = 0; pos < Tpad; ++pos) {
         const bool valid = pos < T;
         const int64_t i = valid ? perm[pos] : 0;
@@ -315,38 +317,38 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     auto w_digits = [&](int64_t g, std::vector<int8_t>& W) {
         const double dl = g < G ? delays[g] : 0.0;
         for (int k = 0; k < Kpad; k += 2) {
-            int q0 = 0, q1 = 0;
+            long long q0 = 0, q1 = 0;
             if (g < G) {
                 if (k < 2 * J) {
                     const int j = k >> 1;
                     const double sn = std::sin(omega[j] * dl), cn = std::cos(omega[j] * dl);
-                    q0 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * cn - b[j] * sn) * sigma, -1.0), 1.0) * 1073741824.0);
-                    q1 = (int)std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * sn + b[j] * cn) * sigma, -1.0), 1.0) * 1073741824.0);
+                    q0 = std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * cn - b[j] * sn) * sigma, -1.0), 1.0) * 274877906944.0);
+                    q1 = std::llrint(std::fmin(std::fmax(kLog2e * (a[j] * sn + b[j] * cn) * sigma, -1.0), 1.0) * 274877906944.0);
                 } else if (std::isfinite(cs)) {
-                    const long long tot = std::llrint(cs * sigma * 1073741824.0);
+                    const long long tot = std::llrint(cs * sigma * 274877906944.0);
                     const long long base = tot / ncrow, rem = tot - base * ncrow;
                     const int i0 = k - 2 * (int)J, i1 = i0 + 1;
                     const long long ar = rem < 0 ? -rem : rem, sg = rem < 0 ? -1 : 1;
-                    q0 = (int)(base + (i0 < ar ? sg : 0));
-                    q1 = (int)(base + (i1 < ar ? sg : 0));
+                    q0 = base + (i0 < ar ? sg : 0);
+                    q1 = base + (i1 < ar ? sg : 0);
                 }
             }
-            split_digits4(q0, W[0 * Kpad + k], W[1 * Kpad + k], W[2 * Kpad + k], W[3 * Kpad + k]);
-            split_digits4(q1, W[0 * Kpad + k + 1], W[1 * Kpad + k + 1], W[2 * Kpad + k + 1], W[3 * Kpad + k + 1]);
+            split_digits5(q0, W[0 * Kpad + k], W[1 * Kpad + k], W[2 * Kpad + k], W[3 * Kpad + k], W[4 * Kpad + k]);
+            split_digits5(q1, W[0 * Kpad + k + 1], W[1 * Kpad + k + 1], W[2 * Kpad + k + 1], W[3 * Kpad + k + 1], W[4 * Kpad + k + 1]);
         }
     };
-    std::vector<int8_t> W((size_t)4 * Kpad);
+    std::vector<int8_t> W((size_t)5 * Kpad);
 
     if (dump_path) {
         // the images in the device's byte order ([plane][k / 16][row][k % 16], constants and flag block behind the Phi planes),
         // to be compared with what the kernels themselves produce (tests/emu/images_emu.cpp)
         const int TM = 128, n_dt = (int)((G + TM - 1) / TM);
         const size_t a_plane = (size_t)Kpad * TM, b_plane = (size_t)Kpad * cfg::TN;
-        const size_t a_bytes = 4 * a_plane, b_bytes = 4 * b_plane + cfg::TN * 16 + 16;
+        const size_t a_bytes = 5 * a_plane, b_bytes = 4 * b_plane + cfg::TN * 16 + 16;
         std::vector<uint8_t> Wi((size_t)n_dt * a_bytes, 0), Pi((size_t)n_bt * b_bytes, 0);
         for (int64_t g = 0; g < (int64_t)n_dt * TM; ++g) {
             w_digits(g, W);
-            for (int pl = 0; pl < 4; ++pl)
+            for (int pl = 0; pl < 5; ++pl)
                 for (int k = 0; k < Kpad; ++k)
                     Wi[(size_t)(g / TM) * a_bytes + pl * a_plane + ((size_t)(k / 16) * TM + g % TM) * 16 + k % 16] = (uint8_t)W[pl * Kpad + k];
         }
@@ -391,25 +393,26 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const bool has_counts = (int64_t)bt * cfg::TN < n_nz;
-                // the ten digit-plane products of the tile (int32, exact), loglik_tc.cu header
+                // the eleven digit-plane products of the tile (int32, exact), loglik_tc.cu header
                 for (int r = 0; r < cfg::TN; ++r) {
                     const size_t pos = (size_t)bt * cfg::TN + r;
                     const int8_t* p1 = &P[((size_t)0 * Tpad + pos) * Kpad];
                     const int8_t* p2 = &P[((size_t)1 * Tpad + pos) * Kpad];
                     const int8_t* p3 = &P[((size_t)2 * Tpad + pos) * Kpad];
                     const int8_t* p4 = &P[((size_t)3 * Tpad + pos) * Kpad];
-                    const int8_t *w1 = &W[0], *w2 = &W[Kpad], *w3 = &W[2 * Kpad], *w4 = &W[3 * Kpad];
-                    int s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+                    const int8_t *w1 = &W[0], *w2 = &W[Kpad], *w3 = &W[2 * Kpad], *w4 = &W[3 * Kpad], *w5 = &W[4 * Kpad];
+                    int s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
                     for (int k = 0; k < Kpad; ++k) {
                         s2 += w1[k] * p1[k];
                         s3 += w2[k] * p1[k] + w1[k] * p2[k];
                         s4 += w3[k] * p1[k] + w2[k] * p2[k] + w1[k] * p3[k];
                         s5 += w4[k] * p1[k] + w3[k] * p2[k] + w2[k] * p3[k] + w1[k] * p4[k];
+                        s6 += w5[k] * p1[k] + (no_p2w4 ? 0 : w4[k] * p2[k]);
                     }
                     S2[r] = s2;
                     S3[r] = s3;
                     S4[r] = s4;
-                    S5[r] = s5;
+                    S5[r] = no_w5 ? s5 : fold_level6(s5, s6);
                 }
                 for (int cg = 0; cg < cfg::GROUPS; ++cg) {
                     const int slot = (int)((tile_seq * cfg::GROUPS + cg) % cfg::EPI_SLOTS);

@@ -82,17 +82,28 @@ def test_config4_sky_grid_full_size(ctx):
     # the best pixel is the one closest to the true direction (the delays of a solar-system-scale IPN are huge)
     assert np.dot(w["ghat"][best], w["g_true"]) == pytest.approx(np.max(w["ghat"] @ w["g_true"]), abs=1e-12)
     rng = np.random.default_rng(0)
-    idx = np.unique(np.concatenate([[best], rng.choice(49152, 5, replace=False)]))
-    exp = orc.loglik_sky_grid(w["counts"], w["time"], w["exposure"], w["nbins"], w["sc_pos"], w["ghat"][idx], w["omega"], w["a"],
-                              w["b"], w["amp"], w["bkg"])
-    # DESIGN.md error model: |dll| ~ 3e-7 sqrt(sum_i r_i^2) with r_i the Poisson residual weight.  At the maximum
-    # (residuals ~ sqrt(n)) that is < 1e-3 nats per detector; a grossly wrong sky pixel sits ~1e6 nats below the maximum,
-    # has residuals of many counts in all 7e5 shifted bins and is only good to ~1e-8 relative (5e-3 nats here).
-    err = np.abs(ll[idx] - exp)[:, 0]
-    near = (exp[:, 0].max() - exp[:, 0]) < 1e4
-    assert near.sum() >= 1 and err[near].max() < 2 * ATOL  # eight detectors summed
-    assert (err / np.abs(exp[:, 0])).max() < 1e-8
+    idx = np.unique(np.concatenate([[best], rng.choice(49152, 11, replace=False)]))
+    from oracle import c_oracle as corc  # the plain-C twin of the numpy oracle (pinned to it in test_c_oracle.py): 100x faster
+
+    corc.build()
+    exp = corc.loglik_sky_grid(w["counts"], w["time"], w["exposure"], w["nbins"], w["sc_pos"], w["ghat"][idx], w["omega"], w["a"],
+                               w["b"], w["amp"], w["bkg"])
+    # 1e-3 nats absolute on the 8-detector sum for EVERY checked pixel: the random ones sit 1e5 - 1e6 nats below the maximum
+    # (every far detector's model is seconds to minutes off there), which is where the fifth W digit plane and the
+    # per-detector share of the tolerance (n_terms) are needed
+    assert np.abs(ll[idx] - exp)[:, 0].max() < ATOL
     assert idx[int(np.argmax(exp[:, 0]))] == best
+    # the device-resident entry point (ipn_loglik_sky_grid_dev) on the same inputs: bit-identical work, no host staging
+    import torch
+
+    dev = {k: torch.from_numpy(np.ascontiguousarray(w[k])).cuda() for k in ("time", "exposure", "counts", "sc_pos", "ghat", "omega", "a", "b", "amp", "bkg")}
+    out = torch.empty((49152, 1), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.loglik_sky_grid_dev(w["nbins"], w["time"].shape[1], dev["time"].data_ptr(), dev["exposure"].data_ptr(), dev["counts"].data_ptr(),
+                            dev["sc_pos"].data_ptr(), 49152, dev["ghat"].data_ptr(), 1, w["omega"].shape[1], dev["omega"].data_ptr(),
+                            dev["a"].data_ptr(), dev["b"].data_ptr(), dev["amp"].data_ptr(), dev["bkg"].data_ptr(), out.data_ptr())
+    ctx.synchronize()
+    assert np.abs(out.cpu().numpy() - ll).max() < 1e-7
 
 
 def test_config5_population_reduced(ctx):

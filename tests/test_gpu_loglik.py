@@ -195,13 +195,8 @@ def test_sky_grid_vs_oracle(ctx):
                               w["b"], w["amp"], w["bkg"])
     assert ll.shape == (48, 2)
     # nside = 2 pixels are ~30 degrees apart: most of them put the burst seconds away from where it is, ll drops by 1e4
-    # nats and the residuals are tens of counts in every bin.  The digit-plane error model is
-    # |d ll| ~ 1e-8 sqrt(sum (n - mu)^2): 1e-3 nats holds wherever the pixel is within ~1e3 nats of the best one (every
-    # pixel a localisation uses), 3e-8 relative everywhere.
-    err = np.abs(ll - exp)
-    near = (exp.max(axis=0, keepdims=True) - exp) < 1.0e3
-    assert near.sum() >= 2 and err[near].max() < ATOL
-    assert (err / np.abs(exp)).max() < 3e-8
+    # nats and the residuals are tens of counts in every bin -- the tolerance is the same 1e-3 nats absolute there
+    assert np.abs(ll - exp).max() < ATOL
     np.testing.assert_array_equal(np.argmax(ll, axis=0), np.argmax(exp, axis=0))
     # a finer look around the true direction: all of these are plausible pixels
     g0 = w["ghat"][int(np.argmax(exp[:, 0]))]
@@ -291,22 +286,18 @@ def test_compensated_epilogue_on_bright_data(ctx, boost, comp_guaranteed):
     idx = np.arange(0, 512, 8)
     exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"],
                                  w["delays"][idx])
-    # keep to the (delay, draw) pairs where the model is not grossly wrong (DESIGN.md error model: the digit-plane term scales
-    # with the residuals; with data this bright even the jittered second draw is thousands of nats off everywhere)
-    near = (exp.max() - exp) < 1.0e3
-    assert near.sum() >= 2
     errs = {}
     ctx.set_option(OPT_LOGLIK_IMPL, 2)
     try:
         for mode in (0, 3, 1, 2):
             ctx.set_option(OPT_HIFI, mode)
             ll = ctx.loglik_delay_grid(*args)
-            errs[mode] = float(np.abs(ll[idx] - exp)[near].max())
+            errs[mode] = float(np.abs(ll[idx] - exp).max())  # every checked (delay, draw), however wrong the model is there
             np.testing.assert_array_equal(np.argmax(ll[idx], axis=0), np.argmax(exp, axis=0))
     finally:
         ctx.set_option(OPT_HIFI, 0)
         ctx.set_option(OPT_LOGLIK_IMPL, 0)
-    print(f"sum n^2 = {sumsq:.3g}: max |dll| near the maximum by epilogue mode (0 auto, 3 compensated, 1 fp64, 2 plain fp32):", errs)
+    print(f"sum n^2 = {sumsq:.3g}: max |dll| by epilogue mode (0 auto, 3 compensated, 1 fp64, 2 plain fp32):", errs)
     assert errs[0] < ATOL and errs[1] < ATOL
     if comp_guaranteed:
         assert errs[3] < ATOL
