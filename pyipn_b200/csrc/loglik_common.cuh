@@ -71,13 +71,17 @@ __device__ __forceinline__ float exp2_poly(float x) {
     return exp2_core(x - (t - kMagic), t);
 }
 
-// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and |xl| < 0.04, for |xh + xl| <= 120: no clamps.
+// 2^(xh + xl) with xh exact (e.g. an integer multiple of a power of two) and xl a small correction (|xl| < 1), for
+// |xh + xl| <= 120: no clamps.
 // The tcgen05 path bounds the exponent per draw instead (tc_draw_kernel: |c| + log2e sum_j |(a_j, b_j)| <= 120, ~40 for a draw
 // of the prior; a draw beyond the bound goes to the fp64 epilogue, whose exp2 needs none), which saves the two FMNMX of
 // every (delay, bin).  The bound also keeps 1 + u below 2^121, so the log refinement below needs no clamp of its own.
 // -DIPN_EPI_CLAMP restores the clamped form (A/B timing).
 __device__ __forceinline__ float exp2_hilo_bounded(float xh, float xl) {
-    const float t = xh + kMagic;
+    // the integer part is taken from xh + xl, not from xh alone: xl (the level-3 and lower sums) reaches a few tenths for
+    // draws with large amplitudes (sigma <= 1/2), and (xh - rint(xh)) + xl would then leave the polynomial's interval --
+    // a systematic error of 1e-8 .. 1e-7 in u that showed as +2e-2 nats on bright, grossly mismatched data
+    const float t = (xh + xl) + kMagic;
     return exp2_core((xh - (t - kMagic)) + xl, t);
 }
 // the clamped form, for callers without a per-draw bound (the FP32-pipe kernel)
