@@ -260,6 +260,7 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     const bool exact_phi = std::getenv("IPN_EMU_EXACT_PHI") != nullptr;
     const bool no_w5 = std::getenv("IPN_EMU_NO_W5") != nullptr;  // experiment: drop the fifth W digit (W to 2^-31 only)
     const bool no_p2w4 = std::getenv("IPN_EMU_NO_P2W4") != nullptr;
+    const bool all_l6 = std::getenv("IPN_EMU_ALL_L6") != nullptr;  // experiment: the two dropped level-6 products as well
     for (int64_t pos = 0; pos < Tpad; ++pos) {
         const bool valid = pos < T;
         const int64_t i = valid ? perm[pos] : 0;
@@ -407,7 +408,7 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
                         s3 += w2[k] * p1[k] + w1[k] * p2[k];
                         s4 += w3[k] * p1[k] + w2[k] * p2[k] + w1[k] * p3[k];
                         s5 += w4[k] * p1[k] + w3[k] * p2[k] + w2[k] * p3[k] + w1[k] * p4[k];
-                        s6 += w5[k] * p1[k] + (no_p2w4 ? 0 : w4[k] * p2[k]);
+                        s6 += w5[k] * p1[k] + (no_p2w4 ? 0 : w4[k] * p2[k]) + (all_l6 ? w3[k] * p3[k] + w2[k] * p4[k] : 0);
                     }
                     S2[r] = s2;
                     S3[r] = s3;
