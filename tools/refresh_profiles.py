@@ -1,6 +1,6 @@
-"""Turn the raw outputs of tools/gpu_session.sh (gpurun_out/) into the tracked summaries under profiles/.
+"""Turn the raw outputs of a GPU session (gpurun_out/[<subdir>/]) into the tracked summaries under profiles/.
 
-    python tools/refresh_profiles.py r01
+    python tools/refresh_profiles.py r02 r2s6      # tag, sub-directory of gpurun_out/
 
 writes profiles/<tag>_bench_n1.json, <tag>_bench_reference_n1.json, <tag>_launches.csv, <tag>_launches_summary.md,
 <tag>_ncu_loglik_tc_kernel.txt and profiles/roofline_latest.json (the DRAM traffic per launch that bench.py reports).
@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "gpurun_out")
+OUT = os.path.join(ROOT, "gpurun_out", sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 
 KEEP = [
@@ -56,7 +56,7 @@ def launches(tag):
     total = sum(t for _, t in tot.values())
     shutil.copy(src, os.path.join(PROF, f"{tag}_launches.csv"))
     with open(os.path.join(PROF, f"{tag}_launches_summary.md"), "w") as f:
-        f.write("# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (B200, --clock-control none)\n")
+        f.write("# ncu launch list of `python bench.py --draws 500 --steps 2 --warmup 1 --no-cpu-baseline` (B200, --clock-control none)\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n\n")
         f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
         for name, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -65,15 +65,15 @@ def launches(tag):
     return tot
 
 
-def ncu(tag):
-    rep = os.path.join(OUT, "prof_bench.ncu-rep")
+def ncu(tag, rep_name="prof_bench.ncu-rep", label="loglik_tc_kernel", what=None, roofline=True):
+    rep = os.path.join(OUT, rep_name)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     head, units, vals = rows[0], rows[1], rows[2]
     rec = {h: (u, v) for h, u, v in zip(head, units, vals)}
-    with open(os.path.join(PROF, f"{tag}_ncu_loglik_tc_kernel.txt"), "w") as f:
-        f.write("# ncu --set full --import-source on capture of the hot kernel inside `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n")
-        f.write("# (third launch of the fp32-epilogue instantiation; one launch = one draw batch of the bench step)\n\n")
+    with open(os.path.join(PROF, f"{tag}_ncu_{label}.txt"), "w") as f:
+        f.write(what or ("# ncu --set full --clock-control none --import-source on capture of the hot kernel inside `python bench.py --draws 500 --steps 2 "
+                         "--warmup 1 --no-cpu-baseline`\n# (third launch of the fp32-epilogue instantiation; one launch = one draw batch of the bench step)\n\n"))
         for k in ("Kernel Name", "Grid Size", "Block Size"):
             f.write(f"{k} [] = {rec[k][1]}\n")
         for k in KEEP:
@@ -85,16 +85,24 @@ def ncu(tag):
         return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
 
     traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+    if not roofline:
+        return traffic
     json.dump({"kernel": "loglik_tc_kernel", "traffic_bytes_per_launch": traffic,
-               "source": f"profiles/{tag}_ncu_loglik_tc_kernel.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch = one draw "
+               "source": f"profiles/{tag}_ncu_{label}.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch = one draw "
                          "batch of the bench step)"}, open(os.path.join(PROF, "roofline_latest.json"), "w"), indent=1)
     return traffic
 
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    shutil.copy(os.path.join(OUT, "bench_n1.json"), os.path.join(PROF, f"{tag}_bench_n1.json"))
-    shutil.copy(os.path.join(OUT, "bench_ref.json"), os.path.join(PROF, f"{tag}_bench_reference_n1.json"))
+    for src, dst in (("bench_n1.json", f"{tag}_bench_n1.json"), ("bench_ref.json", f"{tag}_bench_reference_n1.json")):
+        if os.path.exists(os.path.join(OUT, src)):
+            shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
     tot = launches(tag)
     print("kernels:", len(tot))
-    print("traffic bytes/launch:", ncu(tag))
+    rep = "prof_tc.ncu-rep" if os.path.exists(os.path.join(OUT, "prof_tc.ncu-rep")) else "prof_bench.ncu-rep"
+    print("traffic bytes/launch:", ncu(tag, rep))
+    if os.path.exists(os.path.join(OUT, "prof_simt.ncu-rep")):
+        ncu(tag, "prof_simt.ncu-rep", "loglik_simt_kernel",
+            "# ncu --set full --clock-control none capture of the FP32-pipe kernel (IPN_OPT_LOGLIK_IMPL = 1) inside `python tools/ncu_target.py 1 16`\n"
+            "# (4096 delays x 16 draws x 1e5 bins, hi / lo W table): the CUDA-core baseline the tcgen05 kernel is measured against\n\n", roofline=False)
