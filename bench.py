@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--k", type=int, default=50)
     ap.add_argument("--loglik-impl", type=int, default=0, help="0 auto, 1 FP32-pipe, 2 tcgen05")
     ap.add_argument("--epilogue", type=int, default=0,
-                    help="IPN_OPT_HIFI of the tcgen05 path: 0 auto (default), 1 fp64, 2 fp32, 3 compensated fp32, 4 product (opt-in)")
+                    help="IPN_OPT_HIFI of the tcgen05 path: 0 auto (default), 1 fp64, 2 fp32, 3 compensated fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

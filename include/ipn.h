@@ -43,10 +43,9 @@ extern "C" {
 #define IPN_OPT_LOGLIK_IMPL 1 /* 0 = auto (default), 1 = FP32-pipe contraction, 2 = tcgen05 sliced-integer contraction */
 #define IPN_OPT_PRECISE_W 2   /* FP32-pipe path only: 1 = hi/lo split delay table (default), 0 = single fp32 table */
 #define IPN_OPT_DRAW_BATCH 3  /* max draws per internal batch (bounds the delay-table scratch); 0 = auto     */
-#define IPN_OPT_HIFI 4        /* tcgen05 path epilogue: 0 = auto (per draw: fp32, compensated fp32 when sum n_i^2 > 1e6,
-                                 fp64 when > 4e7), 1 = fp64, 2 = plain fp32, 3 = compensated fp32, 4 = like auto, but the
-                                 draws auto gives to the plain fp32 epilogue take the product epilogue (one logarithm
-                                 per work item instead of one per bin; opt-in until it is measured on the device)      */
+#define IPN_OPT_HIFI 4        /* tcgen05 path epilogue: 0 = auto (per draw: plain fp32; compensated fp32 when the fp32 error model
+                                 predicts more than ~1.5e-4 nats -- n_terms * sum n_i^2 > 6e5 --; fp64 when > 4e7 or when the draw's
+                                 exponent is not bounded by 2^120), 1 = fp64, 2 = plain fp32, 3 = compensated fp32             */
 
 typedef struct ipn_ctx ipn_ctx;
 

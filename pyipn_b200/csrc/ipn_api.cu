@@ -246,8 +246,7 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
             ctx->precise_w = value != 0;
             return IPN_OK;
         case IPN_OPT_HIFI:
-            IPN_REQUIRE(value >= 0 && value <= 4,
-                        "IPN_OPT_HIFI must be 0 (auto), 1 (fp64), 2 (fp32), 3 (compensated fp32) or 4 (product epilogue where it applies)");
+            IPN_REQUIRE(value >= 0 && value <= 3, "IPN_OPT_HIFI must be 0 (auto), 1 (fp64), 2 (fp32) or 3 (compensated fp32)");
             ctx->hifi_mode = (int)value;
             return IPN_OK;
         case IPN_OPT_DRAW_BATCH:

@@ -60,7 +60,7 @@ struct ipn_ctx {
     // options
     int loglik_impl = 0;
     int precise_w = 1;
-    int hifi_mode = 0;  // tcgen05 path epilogue: 0 auto, 1 force fp64, 2 force plain fp32, 3 force compensated fp32, 4 auto + product
+    int hifi_mode = 0;  // tcgen05 path epilogue: 0 auto, 1 force fp64, 2 force plain fp32, 3 force compensated fp32
     int64_t draw_batch = 0;
     int n_terms = 1;    // how many likelihood passes are summed into the caller's result (sky grid: D detectors): the 1e-3 nat
                         // tolerance is shared between them, so the per-draw epilogue choice is made for a 1 / n_terms share

@@ -82,90 +82,6 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
 #endif
 }
 
-// ------------------------------------------------------------------------------------------------------
-// Product epilogue (EPI_PROD): sum_i n_i log2(1 + u_i) = log2 prod_i (1 + u_i)^(n_i).  The running product is carried
-// per thread as 2^E P with P a float64, and ONE logarithm is taken per work item (by the caller) instead of one MUFU.LG2
-// plus its refinement per (delay, bin): multiplying by (1 + u) is  P <- fma(P, u, P)  -- one conversion of u and one DFMA,
-// on pipes the rest of the epilogue does not use (B200 issues FP64 at half the FP32 rate; this is not for sm_103).
-// float64 is what makes it this short: 53 bits keep a u as small as 1e-16 (the tiny-source regime, where fl32(1 + u) = 1
-// would drop the source altogether), the rounding of the product is negligible (what remains is the 2.6e-8 rms of 2^x,
-// random, i.e. ~1e-5 nats over 1e5 bins), and the exponent range lets several multiplications pass between
-// renormalisations: u <= 2^120 (the mode is only selected for draws whose exponent is bounded by 120 -- which also lets
-// 2^x drop its clamps), at most six multiplications un-renormalised in a row -> P < 2^722.
-// Renormalisation: E += exponent(P), exponent field of P reset to 0 -- three integer instructions.
-// The counts of a bin are warp-uniform (one bin per TMEM column, one delay per lane), so the loop over the second, third ...
-// count does not diverge.
-// ------------------------------------------------------------------------------------------------------
-#ifdef IPN_HOST_EMU
-__device__ __forceinline__ int double_hi(double x) {
-    long long b;
-    std::memcpy(&b, &x, 8);
-    return (int)(b >> 32);
-}
-__device__ __forceinline__ double double_with_hi(double x, int hi) {
-    long long b;
-    std::memcpy(&b, &x, 8);
-    b = (b & 0xffffffffll) | ((long long)hi << 32);
-    std::memcpy(&x, &b, 8);
-    return x;
-}
-#else
-__device__ __forceinline__ int double_hi(double x) { return __double2hiint(x); }
-__device__ __forceinline__ double double_with_hi(double x, int hi) { return __hiloint2double(hi, __double2loint(x)); }
-#endif
-
-__device__ __forceinline__ void prod_renorm(double& P, int& E) {
-    const int hi = double_hi(P);  // P >= 1: sign bit clear
-    E += (hi >> 20) - 1023;
-    P = double_with_hi(P, (hi & 0x000fffff) | 0x3ff00000);
-}
-
-// cst[j] = (n, kappa_hi, kappa_lo, n as an INTEGER bit pattern): tc_pimg_kernel writes the last field that way for the
-// draws of this mode (the other epilogues keep n log2e there).
-// NU: what is known about the counts of the eight bins.  In this mode the bins are ordered by their counts (1, 2, 3, then
-// >= 4, then 0: tc_perm_sorted_kernel), so nearly every tile has ONE count value and the multiplications are straight-line
-// code: NU = 1, 2, 3 -> every bin has exactly NU counts; NU = 0 -> no bin has counts (only -kappa u); NU = -1 -> anything
-// (tiles across a class boundary, bins with four or more counts): a loop per bin over its counts, warp-uniform.
-template <int NU>
-__device__ __forceinline__ void epi_units8_prod(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                                const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                                float mks8, float& ssum, float& scomp, double& P, int& E) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 c = cst[j];  // warp-uniform
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo_bounded(xh, xl);  // |x| <= 120 by selection (tc_draw_kernel)
-        v[j] = -fmaf(c.y, u, c.z * u);
-        if (NU > 0) {
-            // u <= 2^120: NU <= 3 multiplications per bin and a renormalisation every second bin keep P < 2^722
-            const double ud = (double)u;
-#pragma unroll
-            for (int k = 0; k < NU; ++k) P = fma(P, ud, P);
-            if (j & 1) prod_renorm(P, E);
-        } else if (NU < 0) {
-            int n = __float_as_int(c.w);
-            if (n > 0) {
-                const double ud = (double)u;
-                P = fma(P, ud, P);
-#pragma unroll 1
-                while (--n > 0) {  // further counts of the same bin
-                    prod_renorm(P, E);
-                    P = fma(P, ud, P);
-                }
-            }
-            if ((j & 3) == 3) prod_renorm(P, E);
-        }
-    }
-    const float g = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    const float yk = g - scomp;
-    const float tt = ssum + yk;
-    scomp = (tt - ssum) - yk;
-    ssum = tt;
-}
-
 // Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
 // not the exponent or the logarithm but three roundings of O(n)-sized quantities: n*y0, kappa*u and their difference
 // (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of eight such terms.  Here the two products and the

@@ -253,7 +253,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // One instantiation per epilogue mode (EPI_FP32 / EPI_COMP / EPI_FP64): each handles only the draws flagged for its mode
 // (every role skips the others' items), so the common fp32 instantiation carries no compensated or fp64 code in its
 // instruction-cache footprint.
-enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, EPI_PROD = 3 };
+enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, N_EPI = 3 };
 // (register budget: 96 per thread -- 19 warps x 32 x 104 does not launch, the allocation granule is 512 registers per warp)
 template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
@@ -514,8 +514,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
-            double pP = 1.0;  // EPI_PROD: running product 2^pE pP of (1 + u)^n over the item's bins
-            int pE = 0;
             double hacc = 0.0;
             const double ksd = (double)ks;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
@@ -529,7 +527,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 tc_fence_after();
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
                 const bool has_counts = cbase[TN].x != 0.0f;
-                const float n_uniform = cbase[TN].y;  // EPI_PROD: the count value all bins of the tile share, 0 = none
                 for (; cg < GROUPS; cg += EPI_SLOTS) {
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
@@ -604,15 +601,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                         for (int h = 0; h < NH; ++h) {
                             if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
-                            else if (MODE == EPI_PROD) {
-#define IPN_PROD_UNITS(NU) epi_units8_prod<NU>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, pP, pE)
-                                if (!has_counts) IPN_PROD_UNITS(0);
-                                else if (n_uniform == 1.0f) IPN_PROD_UNITS(1);
-                                else if (n_uniform == 2.0f) IPN_PROD_UNITS(2);
-                                else if (n_uniform == 3.0f) IPN_PROD_UNITS(3);
-                                else IPN_PROD_UNITS(-1);
-#undef IPN_PROD_UNITS
-                            }
                             else if (MODE == EPI_COMP && has_counts)
                                 epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
@@ -628,7 +616,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 }
             }
             double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
-            if (MODE == EPI_PROD) acc += (double)pE + log2(pP);  // the item's one logarithm
             const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
             if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
         }
@@ -697,42 +684,36 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     int* d_perm = d_nnz + 8;
     double* d_blk_sq = reinterpret_cast<double*>(d_nnz + perm_ints);
     int* d_blk_cnt = reinterpret_cast<int*>(d_blk_sq + n_pblk + 1);
-    if (ctx->hifi_mode == 4) {  // product epilogue: bins ordered by their counts (d_blk_cnt holds four counters per block)
-        if (n_pblk > 0) tc_perm_sorted_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
-        tc_perm_sorted_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm,
-                                                                               d_nnz, ctx->hifi_mode);
-    } else {
-        if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
-        tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm, d_nnz,
-                                                                        ctx->hifi_mode);  // T == 0: only writes the flags
-    }
+    if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
+    tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm, d_nnz,
+                                                                    ctx->hifi_mode);  // T == 0: only writes the flags
     ctx->launches += n_pblk > 0 ? 2 : 1;
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
     uint8_t* d_P = ctx->misc.as<uint8_t>();
     double* d_R = ctx->accum.as<double>();
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
-    void (*kern[4])(const TcParams) = {nullptr, nullptr, nullptr, nullptr};  // by epilogue mode
+    void (*kern[N_EPI])(const TcParams) = {nullptr, nullptr, nullptr};  // by epilogue mode
     switch (ksteps) {
 #define IPN_TC_CASE(K)                            \
     case K:                                       \
         kern[0] = loglik_tc_kernel<K, EPI_FP32>;  \
         kern[1] = loglik_tc_kernel<K, EPI_COMP>;  \
         kern[2] = loglik_tc_kernel<K, EPI_FP64>;  \
-        kern[3] = loglik_tc_kernel<K, EPI_PROD>;  \
         break;
         IPN_TC_CASE(1) IPN_TC_CASE(2) IPN_TC_CASE(3) IPN_TC_CASE(4) IPN_TC_CASE(5) IPN_TC_CASE(6)
         default: IPN_TC_CASE(7)
 #undef IPN_TC_CASE
     }
     // which instantiations can have work: auto -> fp32, compensated and (rarely) fp64; forced modes -> one
-    const int hm = ctx->hifi_mode;  // 4 = product epilogue where it applies, the automatic choice elsewhere
-    const bool run_mode[4] = {hm == 0 || hm == 2 || hm == 4, hm == 0 || hm == 3 || hm == 4, hm == 0 || hm == 1 || hm == 4, hm == 4};
+    // (a draw whose exponent is not bounded goes to the fp64 epilogue whatever the option says, so that one always runs)
+    const int hm = ctx->hifi_mode;
+    const bool run_mode[N_EPI] = {hm == 0 || hm == 2, hm == 0 || hm == 3, true};
     {
         int* trap = trap_record_device_ptr();
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < N_EPI; ++m)
         if (run_mode[m]) IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
@@ -792,7 +773,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                 p.dbg = ctx->dbg.as<unsigned long long>();
             }
             main_kernel_begin(ctx);
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < N_EPI; ++m) {
                 if (!run_mode[m]) continue;
                 // the per-draw modes are decided on the device, so in auto mode all three are launched; an instantiation
                 // without draws of its mode exits at once (~15 us)

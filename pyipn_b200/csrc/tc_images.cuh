@@ -70,7 +70,7 @@ static_assert(L6_COL0 + TN <= ACC_COL0 && PWT * (KPAD_MAX / 4) <= L6_COL0, "tens
 struct TcDraw {
     float ks;     // kappa = 2^-12 / sigma
     float sigma;  // power of two
-    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64, 3 product (EPI_* below)
+    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* in loglik_tc.cu)
     int pad;
 };
 
@@ -114,12 +114,7 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
     const double crit = ysc * ysc * sumsq * (double)(n_terms > 1 ? n_terms : 1);
     t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0))));
-    // flags[1] = 4 (opt-in, IPN_OPT_HIFI = 4): the product epilogue (EPI_PROD, loglik_epilogue.cuh) for the draws the plain
-    // fp32 epilogue would get, provided no exponent can leave [-120, 120] (|x| <= |c| + log2e sum_j |(a_j, b_j)|, the phases
-    // of all frequencies aligned; ~40 for a draw of the prior): that epilogue evaluates 2^x without clamps.  The other
-    // draws keep the automatic choice.
     const bool bounded = (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0;
-    if (flags[1] == 4 && t.hifi == 0 && bounded) t.hifi = 3;
     // the fp32 epilogues evaluate 2^x without clamps (exp2_hilo): a draw whose exponent could leave [-120, 120] -- amplitudes
     // far outside anything the model's priors produce -- is evaluated by the fp64 epilogue whatever the option says
     if (!bounded) t.hifi = 2;
@@ -274,22 +269,11 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
         c.y = khi;
         c.z = (float)(kap - (double)khi);
         c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
-        float n_uniform = 0.0f;
-        if (td[sl].hifi == 3) {
-            // product epilogue: n as an integer, and in the tile's flag block the count value all its bins share (1, 2 or 3;
-            // 0 = mixed, four or more, or padding: the epilogue then loops per bin).  The threads here are rows 0 .. TN - 1.
-            const int n_int = (valid && src) ? (int)min(counts[i], (int64_t)0x7fffffff) : 0;
-            c.w = __int_as_float(n_int);
-            const unsigned act = __activemask();
-            const int n0 = __shfl_sync(act, n_int, 0);
-            if (__all_sync(act, n_int == n0) && n0 >= 1 && n0 <= 3) n_uniform = (float)n0;
-        }
         *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
         if (row == 0) {
             float4 f;
             f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
-            f.y = n_uniform;
-            f.z = f.w = 0.0f;
+            f.y = f.z = f.w = 0.0f;
             *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
         }
     }

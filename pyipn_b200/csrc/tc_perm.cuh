@@ -105,112 +105,4 @@ __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t*
     if (i < T) perm[flag ? nz_before : (int64_t)s_total + (i - nz_before)] = (int)i;
 }
 
-// Count-sorted variant of the permutation for the product epilogue (IPN_OPT_HIFI = 4): bins with one count first, then
-// two, three, four-or-more, and the empty bins last, each class in its original order (a stable counting sort over five
-// classes, same two passes and the same outputs as above).  Nearly every 32-bin tile then holds ONE count value, which
-// tc_pimg_kernel records in the tile's flag block, and the epilogue multiplies (1 + u) that many times in straight-line code.
-__device__ __forceinline__ int count_class(int64_t n) { return n <= 0 ? 4 : (n >= 4 ? 3 : (int)n - 1); }
-
-__global__ void __launch_bounds__(1024) tc_perm_sorted_count_kernel(int64_t T, const int64_t* __restrict__ counts,
-                                                                    int* __restrict__ blk_cnt4, double* __restrict__ blk_sq) {
-    __shared__ int wsum[4][32];
-    __shared__ double wsq[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t i = (int64_t)blockIdx.x * 1024 + tid;
-    const int64_t ni = (i < T) ? counts[i] : 0;
-    const int cls = count_class(ni);
-    double sq = (double)ni * (double)ni;
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = __popc(__ballot_sync(0xffffffffu, cls == k));
-        if (lane == 0) wsum[k][warp] = c;
-    }
-    if (lane == 0) wsq[warp] = sq;
-    __syncthreads();
-    if (tid < 4) {
-        int t = 0;
-        for (int w = 0; w < 32; ++w) t += wsum[tid][w];
-        blk_cnt4[blockIdx.x * 4 + tid] = t;
-    }
-    if (tid == 0) {
-        double q = 0.0;
-        for (int w = 0; w < 32; ++w) q += wsq[w];
-        blk_sq[blockIdx.x] = q;
-    }
-}
-
-__global__ void __launch_bounds__(1024) tc_perm_sorted_kernel(int64_t T, const int64_t* __restrict__ counts, int n_blk,
-                                                              const int* __restrict__ blk_cnt4, const double* __restrict__ blk_sq,
-                                                              int* __restrict__ perm, int* __restrict__ n_nz_out, int hifi_mode) {
-    __shared__ int s_before[4], s_total[4];  // bins of class k in the blocks before this one / in all blocks
-    __shared__ int wcnt[4][32];              // bins of class k in each warp of this block
-    __shared__ double s_sq;
-    __shared__ int wred[8][32];
-    __shared__ double wsq[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        // per class: bins in the blocks before this one, and in all blocks (integer sums: exact, order-independent)
-        int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [k] = before, [4 + k] = total
-        double sq = 0.0;
-        for (int b = tid; b < n_blk; b += 1024) {
-            const int* c = blk_cnt4 + (size_t)b * 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                acc[4 + k] += c[k];
-                if (b < (int)blockIdx.x) acc[k] += c[k];
-            }
-            sq += blk_sq[b];  // integers below 2^53: exact as well
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            int x = acc[q];
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0) wred[q][warp] = x;
-        }
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0) wsq[warp] = sq;
-        __syncthreads();
-        if (tid < 8) {
-            int t = 0;
-            for (int w = 0; w < 32; ++w) t += wred[tid][w];
-            if (tid < 4) s_before[tid] = t; else s_total[tid - 4] = t;
-        }
-        if (tid == 32) {
-            double q = 0.0;
-            for (int w = 0; w < 32; ++w) q += wsq[w];
-            s_sq = q;
-        }
-    }
-    const int64_t i = (int64_t)blockIdx.x * 1024 + tid;
-    const int cls = (i < T) ? count_class(counts[i]) : 4;
-    int rank = 0;  // bins of my class before me in my warp
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
-        if (lane == 0) wcnt[k][warp] = __popc(m);
-        if (cls == k) rank = __popc(m & ((1u << lane) - 1u));
-    }
-    const unsigned mnz = __ballot_sync(0xffffffffu, cls != 4);
-    const int nz_lane = __popc(mnz & ((1u << lane) - 1u));  // bins with counts before me in my warp
-    __syncthreads();
-    const int n_nz = s_total[0] + s_total[1] + s_total[2] + s_total[3];
-    if (blockIdx.x == 0 && tid == 0) {
-        n_nz_out[0] = n_nz;
-        n_nz_out[1] = hifi_mode;
-        *reinterpret_cast<double*>(n_nz_out + 2) = s_sq;  // sum n_i^2, read by tc_draw_kernel for the per-draw epilogue choice
-    }
-    if (i >= T) return;
-    if (cls < 4) {
-        int pos = s_before[cls] + rank;
-        for (int k = 0; k < cls; ++k) pos += s_total[k];         // classes sorted before mine
-        for (int w = 0; w < warp; ++w) pos += wcnt[cls][w];      // my class in the warps before mine
-        perm[pos] = (int)i;
-    } else {
-        int nz_before = s_before[0] + s_before[1] + s_before[2] + s_before[3] + nz_lane;
-        for (int w = 0; w < warp; ++w) nz_before += wcnt[0][w] + wcnt[1][w] + wcnt[2][w] + wcnt[3][w];
-        perm[(int64_t)n_nz + (i - nz_before)] = (int)i;
-    }
-}
-
 }  // namespace ipn

@@ -4,7 +4,7 @@
 // byte as the device would lay them out.  tests/test_emu.py compares them with what `tc_emu images` -- the restatement the
 // full-size emulation runs on -- produces for the same problem.
 //
-//   images_emu <in.bin> <IPN_OPT_HIFI: 0 | 4> <out.bin>
+//   images_emu <in.bin> <out.bin>
 #include "cuda_shim.h"
 
 #include "../../pyipn_b200/csrc/tc_images.cuh"
@@ -15,8 +15,8 @@ static bool rd(FILE* f, T* p, size_t n) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 4) return 64;
-    const int hifi_mode = std::atoi(argv[2]);
+    if (argc < 3) return 64;
+    const int hifi_mode = 0;
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) return 2;
     int64_t hdr[3];
@@ -48,15 +48,9 @@ int main(int argc, char** argv) {
     std::vector<int> blk_cnt((size_t)(n_pblk + 1) * 4), perm((size_t)T + 1);
     std::vector<double> blk_sq((size_t)n_pblk + 1);
     alignas(8) int flags[4] = {0, 0, 0, 0};
-    if (hifi_mode == 4) {
-        if (n_pblk > 0) shim::launch(tc_perm_sorted_count_kernel, n_pblk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
-        shim::launch(tc_perm_sorted_kernel, n_pblk > 0 ? n_pblk : 1, 1024, T, counts.data(), n_pblk, blk_cnt.data(), blk_sq.data(),
-                     perm.data(), flags, hifi_mode);
-    } else {
-        if (n_pblk > 0) shim::launch(tc_perm_count_kernel, n_pblk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
-        shim::launch(tc_perm_kernel, n_pblk > 0 ? n_pblk : 1, 1024, T, counts.data(), n_pblk, blk_cnt.data(), blk_sq.data(), perm.data(),
-                     flags, hifi_mode);
-    }
+    if (n_pblk > 0) shim::launch(tc_perm_count_kernel, n_pblk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
+    shim::launch(tc_perm_kernel, n_pblk > 0 ? n_pblk : 1, 1024, T, counts.data(), n_pblk, blk_cnt.data(), blk_sq.data(), perm.data(),
+                 flags, hifi_mode);
     TcDraw td;
     shim::launch(tc_draw_kernel, 1, 128, (int64_t)0, 1, (int)J, Kpad - 2 * (int)J, a.data(), b.data(), &dc, flags, 1, &td);
     std::vector<uint8_t> W((size_t)n_dt * a_bytes + 16, 0xAB), P((size_t)n_bt * b_bytes + 16, 0xAB);
@@ -71,7 +65,7 @@ int main(int argc, char** argv) {
                       counts.data(), perm.data(), flags, omega.data(), &dc, &td, (const PhiTabEntry*)phitab.data(), n_bt, b_bytes,
                       b_plane, Pp);
 
-    FILE* g = std::fopen(argv[3], "wb");
+    FILE* g = std::fopen(argv[2], "wb");
     if (!g) return 2;
     const int ih[4] = {Kpad, n_dt, n_bt, td.hifi};
     const float fh[2] = {td.ks, td.sigma};

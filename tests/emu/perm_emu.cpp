@@ -1,8 +1,7 @@
 // The bin-permutation kernels of the tcgen05 likelihood path (pyipn_b200/csrc/tc_perm.cuh), compiled for the HOST: test
 // infrastructure.  A small shim gives every CUDA thread of a block its own OS thread, __syncthreads a real barrier and the
 // warp collectives (__shfl_xor_sync, __ballot_sync, ...) a per-warp exchange, so the kernels run here from their own
-// source, block after block, exactly as written -- and are checked against std::stable_sort.  This is how the count-sorted
-// permutation of the opt-in product epilogue (written after the round's GPU minutes were spent) got its first execution.
+// source, block after block, exactly as written -- and are checked against std::stable_sort.
 //
 //   perm_emu <T> <seed> <mean counts per bin>   ->  "ok ..." or a description of the first mismatch (exit code 1)
 #include <algorithm>
@@ -71,15 +70,6 @@ int main(int argc, char** argv) {
                  flags, 0);
     if (check("tc_perm_kernel", want, 0)) return 1;
 
-    // the count-sorted permutation of the product epilogue: classes 1, 2, 3, >= 4, then 0, each in its original order
-    std::fill(perm.begin(), perm.end(), -1);
-    std::fill(blk_cnt.begin(), blk_cnt.end(), -7);
-    for (int64_t i = 0; i < T; ++i) want[i] = (int)i;  // from the identity again: independent of the partition above
-    std::stable_sort(want.begin(), want.end(), [&](int a, int b) { return cls_of(counts[a]) < cls_of(counts[b]); });
-    if (n_blk > 0) shim::launch(ipn::tc_perm_sorted_count_kernel, n_blk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
-    shim::launch(ipn::tc_perm_sorted_kernel, n_blk > 0 ? n_blk : 1, 1024, T, counts.data(), n_blk, blk_cnt.data(), blk_sq.data(),
-                 perm.data(), flags, 4);
-    if (check("tc_perm_sorted_kernel", want, 4)) return 1;
     std::printf("ok T=%lld blocks=%d n_nz=%lld\n", (long long)T, n_blk, (long long)n_nz);
     return 0;
 }

@@ -14,8 +14,7 @@
 //
 //   tc_emu funcs                          -> JSON with error statistics of exp2_poly / exp2_hilo / sincos_* / poisson_term
 //   tc_emu grid <in.bin> <bias> <noise>   -> for every delay: ll by the fp32, compensated fp32 and fp64 epilogues
-//   tc_emu gridprod <in.bin>              -> for every delay: ll by the product epilogue (count-sorted bins, IPN_OPT_HIFI = 4)
-//   tc_emu images <in.bin> <0 | 4> <out>   -> the restated operand images in the device's byte order (cf. images_emu.cpp)
+//   tc_emu images <in.bin> <out>          -> the restated operand images in the device's byte order (cf. images_emu.cpp)
 //   tc_emu rff <in.bin> <out.bin>         -> rff_eval_kernel's arithmetic (rff_terms.cuh): lambda (S, T) float64 + the tier of every draw
 #include <cmath>
 #include <cstdint>
@@ -162,7 +161,7 @@ static bool rd(FILE* f, T* p, size_t n) {
     return std::fread(p, sizeof(T), n, f) == n;
 }
 
-static int run_grid(const char* path, double bias, double noise, bool prod, const char* dump_path = nullptr) {
+static int run_grid(const char* path, double bias, double noise, const char* dump_path = nullptr) {
     g_lg2_bias = bias;
     g_lg2_noise = noise;
     FILE* f = std::fopen(path, "rb");
@@ -218,23 +217,16 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
     const float sigma_f = (float)std::ldexp(1.0, e), ks = (float)std::ldexp(1.0, -12 - e);
     const double ysc = std::isfinite(cabs) ? std::fmax(1.0, (double)dc.c_hi) : 1.0;
     const double crit = ysc * ysc * sumsq;
-    // IPN_OPT_HIFI = 4: the product epilogue where the plain fp32 one would run; a draw whose exponent could leave [-120, 120]
-    // is evaluated by the fp64 epilogue whatever the option says (the fp32 epilogues evaluate 2^x without clamps)
+    // a draw whose exponent could leave [-120, 120] is evaluated by the fp64 epilogue whatever the option says (the fp32
+    // epilogues evaluate 2^x without clamps)
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
     const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0));  // n_terms = 1
-    const int prod_mode = (auto_mode == 0 && xmax <= 120.0) ? 3 : auto_mode;
 
-    // tc_perm_kernel: bins with counts first (stable); tc_perm_sorted_kernel (product epilogue): by count class 1, 2, 3, >= 4, 0
+    // tc_perm_kernel: bins with counts first (stable)
     std::vector<int> perm;
     perm.reserve(T);
-    if (prod) {
-        for (int cls = 0; cls < 4; ++cls)
-            for (int64_t i = 0; i < T; ++i)
-                if ((counts[i] <= 0 ? 4 : (counts[i] >= 4 ? 3 : (int)counts[i] - 1)) == cls) perm.push_back((int)i);
-    } else {
-        for (int64_t i = 0; i < T; ++i)
-            if (counts[i] > 0) perm.push_back((int)i);
-    }
+    for (int64_t i = 0; i < T; ++i)
+        if (counts[i] > 0) perm.push_back((int)i);
     const int64_t n_nz = (int64_t)perm.size();
     for (int64_t i = 0; i < T; ++i)
         if (!(counts[i] > 0)) perm.push_back((int)i);
@@ -296,19 +288,8 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
         cc.y = khi;
         cc.z = (float)(kap - (double)khi);
         cc.w = cc.x * 1.44269504f;
-        if (prod && prod_mode == 3) cc.w = __int_as_float((valid && src) ? (int)std::min<int64_t>(counts[i], 0x7fffffff) : 0);
         cst[pos] = cc;
     }
-    // tile flag block of the product epilogue: the count value all 32 bins share (1, 2, 3), else 0
-    std::vector<int> n_uniform(n_bt, 0);
-    if (prod && prod_mode == 3)
-        for (int bt = 0; bt < n_bt; ++bt) {
-            const int n0 = __float_as_int(cst[(size_t)bt * cfg::TN].w);
-            bool all = n0 >= 1 && n0 <= 3;
-            for (int r = 0; r < cfg::TN && all; ++r) all = __float_as_int(cst[(size_t)bt * cfg::TN + r].w) == n0;
-            n_uniform[bt] = all ? n0 : 0;
-        }
-
     const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
     const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
     const double ksd = (double)ks, sigma = (double)sigma_f;
@@ -361,13 +342,13 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
                     img[pl * b_plane + ((size_t)(k / 16) * cfg::TN + row) * 16 + k % 16] = (uint8_t)P[((size_t)pl * Tpad + pos) * Kpad + k];
             std::memcpy(img + 4 * b_plane + (size_t)row * 16, &cst[pos], 16);
             if (row == 0) {
-                const float4 fl = {(pos < n_nz) ? 1.0f : 0.0f, (float)n_uniform[pos / cfg::TN], 0.0f, 0.0f};
+                const float4 fl = {(pos < n_nz) ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
                 std::memcpy(img + 4 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
             }
         }
         FILE* g = std::fopen(dump_path, "wb");
         if (!g) return 2;
-        const int ih[4] = {Kpad, n_dt, n_bt, prod ? prod_mode : auto_mode};
+        const int ih[4] = {Kpad, n_dt, n_bt, auto_mode};
         const float fh[2] = {ks, sigma_f};
         std::fwrite(ih, 4, 4, g);
         std::fwrite(fh, 4, 2, g);
@@ -377,19 +358,16 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
         return 0;
     }
 
-    std::printf("{\"auto_mode\": %d, \"prod_mode\": %d, \"xmax\": %.6g, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
-                auto_mode, prod_mode, xmax, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
+    std::printf("{\"auto_mode\": %d, \"xmax\": %.6g, \"sigma\": %g, \"Kpad\": %d, \"n_nz\": %lld, \"nchunk\": %d, \"sumsq\": %.17g,\n\"ll\": [\n",
+                auto_mode, xmax, sigma, Kpad, (long long)n_nz, nchunk, sumsq);
     std::vector<int> S2(cfg::TN), S3(cfg::TN), S4(cfg::TN), S5(cfg::TN);
     for (int64_t g = 0; g < G; ++g) {
         w_digits(g, W);
-        double R[4] = {0.0, 0.0, 0.0, 0.0};  // per epilogue mode (fp32, compensated, fp64, product), the float64 atomicAdd target
+        double R[3] = {0.0, 0.0, 0.0};  // per epilogue mode (fp32, compensated, fp64), the float64 atomicAdd target
         for (int chunk = 0; chunk < nchunk; ++chunk) {
             const int bt0 = chunk * tiles_per_chunk, bt1 = std::min(n_bt, bt0 + tiles_per_chunk);
             // per item: one (ssum, scomp, slo) per epilogue warp of the lane quarter (slot), for each fp32 mode
-            float ssum[3][cfg::EPI_SLOTS] = {}, scomp[3][cfg::EPI_SLOTS] = {}, slo[2][cfg::EPI_SLOTS] = {};
-            double pP[cfg::EPI_SLOTS];
-            int pE[cfg::EPI_SLOTS] = {};
-            for (int s = 0; s < cfg::EPI_SLOTS; ++s) pP[s] = 1.0;
+            float ssum[2][cfg::EPI_SLOTS] = {}, scomp[2][cfg::EPI_SLOTS] = {}, slo[2][cfg::EPI_SLOTS] = {};
             double hacc[cfg::EPI_SLOTS] = {};
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
@@ -427,16 +405,6 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
                             t5[j] = S5[o + j];
                         }
                         const float4* cp = &cst[(size_t)bt * cfg::TN + o];
-                        if (prod && prod_mode == 3) {
-#define EMU_PROD_UNITS(NU) epi_units8_prod<NU>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[2][slot], scomp[2][slot], pP[slot], pE[slot])
-                            if (!has_counts) EMU_PROD_UNITS(0);
-                            else if (n_uniform[bt] == 1) EMU_PROD_UNITS(1);
-                            else if (n_uniform[bt] == 2) EMU_PROD_UNITS(2);
-                            else if (n_uniform[bt] == 3) EMU_PROD_UNITS(3);
-                            else EMU_PROD_UNITS(-1);
-#undef EMU_PROD_UNITS
-                            continue;
-                        }
                         if (has_counts) {
                             epi_units8<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
                             epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
@@ -451,18 +419,16 @@ static int run_grid(const char* path, double bias, double noise, bool prod, cons
             for (int s = 0; s < cfg::EPI_SLOTS; ++s) {
                 for (int m = 0; m < 2; ++m) R[m] += ((double)ssum[m][s] - (double)scomp[m][s]) + (double)slo[m][s];
                 R[2] += hacc[s];
-                R[3] += ((double)ssum[2][s] - (double)scomp[2][s]) + ((double)pE[s] + std::log2(pP[s]));
             }
         }
         // finalize_kernel
         std::printf("[");
-        // gridprod: what IPN_OPT_HIFI = 4 returns -- the product epilogue if the draw qualifies, else the automatic choice
-        for (int m = prod ? prod_mode : 0; m < (prod ? prod_mode + 1 : 3); ++m) {
+        for (int m = 0; m < 3; ++m) {
             const double v = dc.C + kLn2 * R[m];
             if (std::isfinite(v))
-                std::printf("%.17g%s", v, (m < 2 && !prod) ? ", " : "");
+                std::printf("%.17g%s", v, m < 2 ? ", " : "");
             else  // JSON spelling python's json module accepts
-                std::printf("%s%s", std::isnan(v) ? "NaN" : (v < 0 ? "-Infinity" : "Infinity"), (m < 2 && !prod) ? ", " : "");
+                std::printf("%s%s", std::isnan(v) ? "NaN" : (v < 0 ? "-Infinity" : "Infinity"), m < 2 ? ", " : "");
         }
         std::printf("]%s\n", g + 1 < G ? "," : "");
     }
@@ -533,10 +499,9 @@ static int run_rff(const char* path, const char* out_path) {
 
 int main(int argc, char** argv) {
     if (argc >= 2 && !std::strcmp(argv[1], "funcs")) return run_funcs();
-    if (argc >= 5 && !std::strcmp(argv[1], "grid")) return run_grid(argv[2], std::atof(argv[3]), std::atof(argv[4]), false);
-    if (argc >= 3 && !std::strcmp(argv[1], "gridprod")) return run_grid(argv[2], 0.0, 0.0, true);
-    if (argc >= 5 && !std::strcmp(argv[1], "images")) return run_grid(argv[2], 0.0, 0.0, std::atoi(argv[3]) == 4, argv[4]);
+    if (argc >= 5 && !std::strcmp(argv[1], "grid")) return run_grid(argv[2], std::atof(argv[3]), std::atof(argv[4]));
+    if (argc >= 4 && !std::strcmp(argv[1], "images")) return run_grid(argv[2], 0.0, 0.0, argv[3]);
     if (argc >= 4 && !std::strcmp(argv[1], "rff")) return run_rff(argv[2], argv[3]);
-    std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise> | tc_emu gridprod <in.bin> | tc_emu rff <in.bin> <out.bin>\n");
+    std::fprintf(stderr, "usage: tc_emu funcs | tc_emu grid <in.bin> <lg2 bias> <lg2 noise> | tc_emu images <in.bin> <out.bin> | tc_emu rff <in.bin> <out.bin>\n");
     return 64;
 }

@@ -38,7 +38,7 @@ def emu():
     return EXE
 
 
-def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, counts=None, prod=False):
+def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, counts=None):
     counts = w["counts"] if counts is None else counts
     amp = float(w["amp"][s]) if amp is None else amp
     path = os.path.join(tmp_path, "in.bin")
@@ -48,7 +48,7 @@ def _run_grid(exe, tmp_path, w, s, delays, bias=4e-8, noise=6e-8, amp=None, coun
         for arr, dt in ((w["time"], np.float64), (w["exposure"], np.float64), (counts, np.int64), (w["omega"][s], np.float64),
                         (w["a"][s], np.float64), (w["b"][s], np.float64), (delays, np.float64)):
             np.ascontiguousarray(arr, dtype=dt).tofile(f)
-    cmd = [exe, "gridprod", path] if prod else [exe, "grid", path, repr(bias), repr(noise)]
+    cmd = [exe, "grid", path, repr(bias), repr(noise)]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     res = json.loads(out)
     ref = corc.loglik_delay_grid(counts, w["time"], w["exposure"], w["omega"][s:s + 1], w["a"][s:s + 1], w["b"][s:s + 1],
@@ -251,64 +251,6 @@ def test_rff_phase_beyond_the_fp32_reduction_takes_the_fp64_path(emu, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# product epilogue (IPN_OPT_HIFI = 4, opt-in until measured on the device): count-sorted bins, one logarithm per work item
-# ---------------------------------------------------------------------------------------------------------------
-def test_product_epilogue_full_size(emu, tmp_path):
-    """BASELINE config 2 shape through the product pipeline (count-sorted permutation, per-tile count flags, float64
-    running product): closer to the oracle than the per-bin logarithm it replaces, same arg-max."""
-    w = synth.delay_grid_workload(T=100_000, G=4096, S=1)
-    g_true = int(np.argmin(np.abs(w["delays"] - w["true_delay"])))
-    idx = np.unique(np.concatenate([np.arange(g_true - 4, g_true + 5), [0, 511, 1777, 3000, 4095]]))
-    res, llp, ref = _run_grid(emu, str(tmp_path), w, 0, w["delays"][idx], prod=True)
-    assert res["prod_mode"] == 3
-    err = llp[:, 0] - ref
-    assert np.abs(err).max() < 4e-4 and np.sqrt(np.mean(err ** 2)) < 2.5e-4, err
-    assert idx[np.argmax(llp[:, 0])] == idx[np.argmax(ref)]
-
-
-def test_product_epilogue_count_classes_and_edges(emu, tmp_path):
-    """Bins with 0 ... 40 counts (all five count classes, the per-bin loop, tiles across class boundaries), ragged T, zero
-    exposures, a tiny source (u ~ 1e-9: fl32(1 + u) = 1, the float64 product must keep it) and amp = 0."""
-    rng = np.random.default_rng(7)
-    for T, bright in ((1000 + 17, 1.0), (333, 30.0), (64, 1.0), (5, 1.0)):
-        w = synth.delay_grid_workload(T=T, G=8, S=1, bkg=500.0 * bright, boost=400.0 * bright)
-        d = w["delays"][[0, 5]]
-        _, llp, ref = _run_grid(emu, str(tmp_path), w, 0, d, prod=True)
-        assert np.abs(llp[:, 0] - ref).max() < 2e-4 * bright, (T, bright, llp[:, 0] - ref)
-    w = synth.delay_grid_workload(T=4000, G=8, S=1)
-    d = w["delays"][[1, 6]]
-    for amp in (4e-7, 0.0):  # u ~ 1e-9 everywhere; background only
-        _, llp, ref = _run_grid(emu, str(tmp_path), w, 0, d, amp=amp, prod=True)
-        assert np.abs(llp[:, 0] - ref).max() < 2e-5, (amp, llp[:, 0] - ref)
-        _, ll, _ = _run_grid(emu, str(tmp_path), w, 0, d, amp=amp)
-        assert np.abs(ll[:, 0] - ref).max() < 2e-5
-    # the source term itself (ll - ll(amp = 0)) of the tiny source is resolved, not rounded away
-    _, lt, rt = _run_grid(emu, str(tmp_path), w, 0, d, amp=4e-7, prod=True)
-    _, l0, r0 = _run_grid(emu, str(tmp_path), w, 0, d, amp=0.0, prod=True)
-    np.testing.assert_allclose(lt[:, 0] - l0[:, 0], rt - r0, rtol=5e-2, atol=1e-9)
-    assert np.abs(rt - r0).max() > 1e-8
-    # counts in a bin of zero exposure: -inf from the constant term, whatever the epilogue
-    cz = w["counts"].copy()
-    ez = w["exposure"].copy()
-    ez[10] = 0.0
-    cz[10] = 3
-    wz = dict(w, exposure=ez, counts=cz)
-    _, llz, refz = _run_grid(emu, str(tmp_path), wz, 0, d, prod=True)
-    assert np.isneginf(refz).all() and np.isneginf(llz[:, 0]).all()
-
-
-def test_product_epilogue_is_not_selected_beyond_its_exponent_bound(emu, tmp_path):
-    """The product epilogue evaluates 2^x without clamps: tc_draw_kernel only selects it when |c| + log2e sum_j |(a_j, b_j)|
-    <= 120 (a draw of the prior: ~40); four times the amplitudes and the draw keeps the automatic choice."""
-    w = synth.delay_grid_workload(T=2000, G=8, S=1)
-    res, _, _ = _run_grid(emu, str(tmp_path), w, 0, w["delays"][:1], prod=True)
-    assert res["prod_mode"] == 3 and res["xmax"] < 60
-    big = dict(w, a=4.0 * w["a"], b=4.0 * w["b"])
-    res, _, _ = _run_grid(emu, str(tmp_path), big, 0, w["delays"][:1], prod=True)
-    assert res["xmax"] > 120 and res["prod_mode"] == res["auto_mode"]
-
-
-# ---------------------------------------------------------------------------------------------------------------
 # the bin-permutation kernels themselves (pyipn_b200/csrc/tc_perm.cuh), compiled for the host with a CUDA-thread shim
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
@@ -325,10 +267,9 @@ def perm_emu():
 @pytest.mark.parametrize("T,seed,mean", [(0, 1, 0.9), (1, 2, 0.9), (31, 3, 0.9), (1024, 4, 0.9), (1025, 5, 2.0), (4100, 6, 0.8),
                                           (3333, 7, 0.1), (2500, 8, 6.0)])
 def test_permutation_kernels_run_from_their_own_source(perm_emu, T, seed, mean):
-    """tc_perm_kernel (bins with counts first) and tc_perm_sorted_kernel (count classes 1, 2, 3, >= 4, 0 -- the product
-    epilogue's order): every CUDA thread an OS thread, real barriers and warp collectives; result = std::stable_sort, flags
-    (bins with counts, mode, sum n^2) exact, nothing written past the end.  Empty input, partial blocks, several blocks,
-    sparse and bright data."""
+    """tc_perm_kernel (bins with counts first): every CUDA thread an OS thread, real barriers and warp collectives; result =
+    std::stable_sort, flags (bins with counts, mode, sum n^2) exact, nothing written past the end.  Empty input, partial
+    blocks, several blocks, sparse and bright data."""
     r = subprocess.run([perm_emu, str(T), str(seed), str(mean)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
 
@@ -353,8 +294,7 @@ def images_emu():
 def test_restated_images_equal_the_kernels_own(emu, images_emu, tmp_path, T, G, kw):
     """tc_perm*_kernel, tc_draw_kernel, tc_wimg_kernel and tc_pimg_kernel run on the host from their own source (every CUDA
     thread an OS thread): scale, epilogue choice, W image, Phi image, per-bin constants and tile flags are byte for byte what
-    the restatement inside tc_emu builds -- for the default partition and for the product epilogue's count-sorted order
-    (integer counts and the per-tile count flag).  So the full-size emulation above runs on the images the device builds."""
+    the restatement inside tc_emu builds.  So the full-size emulation above runs on the images the device builds."""
     w = synth.delay_grid_workload(T=T, G=G, S=1, **kw)
     path = os.path.join(str(tmp_path), "in.bin")
     with open(path, "wb") as f:
@@ -363,12 +303,9 @@ def test_restated_images_equal_the_kernels_own(emu, images_emu, tmp_path, T, G, 
         for arr, dt in ((w["time"], np.float64), (w["exposure"], np.float64), (w["counts"], np.int64), (w["omega"][0], np.float64),
                         (w["a"][0], np.float64), (w["b"][0], np.float64), (w["delays"], np.float64)):
             np.ascontiguousarray(arr, dtype=dt).tofile(f)
-    modes = set()
-    for mode in (0, 4):
-        a, b = os.path.join(str(tmp_path), "restated.bin"), os.path.join(str(tmp_path), "kernels.bin")
-        subprocess.run([emu, "images", path, str(mode), a], check=True)
-        subprocess.run([images_emu, path, str(mode), b], check=True, timeout=600)
-        A, B = np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)
-        assert A.size == B.size and np.array_equal(A, B), (mode, A.size, B.size, np.nonzero(A != B)[0][:8] if A.size == B.size else None)
-        modes.add(int(B[:16].view(np.int32)[3]))
-    assert modes <= {0, 1, 2, 3} and (3 in modes) == (0 in modes)  # mode 4 turns exactly the plain-fp32 draws into product draws
+    a, b = os.path.join(str(tmp_path), "restated.bin"), os.path.join(str(tmp_path), "kernels.bin")
+    subprocess.run([emu, "images", path, a], check=True)
+    subprocess.run([images_emu, path, b], check=True, timeout=600)
+    A, B = np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)
+    assert A.size == B.size and np.array_equal(A, B), (A.size, B.size, np.nonzero(A != B)[0][:8] if A.size == B.size else None)
+    assert int(B[:16].view(np.int32)[3]) in (0, 1, 2)

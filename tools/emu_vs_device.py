@@ -41,14 +41,6 @@ def main():
             dev[:, col] = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"],
                                                 w["bkg"], w["delays"])[idx, 0]
     names = ["fp32", "compensated fp32", "fp64"]
-    if "--prod" in sys.argv:  # the opt-in product epilogue (IPN_OPT_HIFI = 4) and its emulation as a fourth column
-        _, emu_p, _ = te._run_grid(exe, tempfile.mkdtemp(), w, 0, w["delays"][idx], prod=True)
-        with Context(0) as ctx:
-            ctx.set_option(OPT_HIFI, 4)
-            dev_p = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"],
-                                          w["delays"])[idx, :1]
-        emu, dev = np.concatenate([emu, emu_p], axis=1), np.concatenate([dev, dev_p], axis=1)
-        names.append("product")
     out = {"workload": "config2: 4096 delays x 1e5 bins, K=50, 1 draw; 48 delays compared", "epilogues": names}
     for name, x, y in (("device_minus_emulation", dev, emu), ("device_minus_oracle", dev, ref[:, None]),
                        ("emulation_minus_oracle", emu, ref[:, None])):
