@@ -47,6 +47,11 @@ extern "C" {
                                  predicts more than ~1.5e-4 nats -- n_terms * sum n_i^2 > 6e5 --; fp64 when > 4e7 or when the draw's
                                  exponent is not bounded by 2^120), 1 = fp64, 2 = plain fp32, 3 = compensated fp32             */
 
+#define IPN_OPT_RFF_IMPL 5    /* ipn_rff_eval: 0 = auto (default: the tcgen05 contraction when the bins are uniform -- time[i] =
+                                 time[0] + i dt, what np.arange edges give --, T >= 1024 and J <= 108, else the direct kernel; the
+                                 _dev entry point checks the spacing on the device, one 24-byte read-back), 1 = direct kernel,
+                                 2 = contraction without the check (the caller guarantees uniform bins)                      */
+
 typedef struct ipn_ctx ipn_ctx;
 
 /* ---- context -------------------------------------------------------------------------------------- */
@@ -68,6 +73,8 @@ double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx);
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches);
 /* which contraction back-end the most recent log-likelihood call used: 1 = FP32 pipe, 2 = tcgen05 (0 = none yet) */
 int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx);
+/* which kernel the most recent ipn_rff_eval call ran: 1 = direct, 2 = tcgen05 contraction on uniform bins (0 = none yet) */
+int ipn_ctx_last_rff_impl(const ipn_ctx* ctx);
 /* draws per internal batch of the most recent log-likelihood call (the operand-image scratch is bounded, so a call with many
  * draws is processed in batches; bench.py spreads its oracle spot check over every batch) */
 int64_t ipn_ctx_last_draw_batch(const ipn_ctx* ctx);

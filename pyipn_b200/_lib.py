@@ -27,11 +27,12 @@ OPT_LOGLIK_IMPL = 1
 OPT_PRECISE_W = 2
 OPT_DRAW_BATCH = 3
 OPT_HIFI = 4
+OPT_RFF_IMPL = 5
 
 # every symbol include/ipn.h declares (tests/test_abi.py checks the list against the header and the .so)
 EXPORTS = (
     "ipn_ctx_create", "ipn_ctx_destroy", "ipn_ctx_set_stream", "ipn_ctx_use_own_stream", "ipn_ctx_synchronize", "ipn_ctx_set_option",
-    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_ctx_last_draw_batch", "ipn_last_error", "ipn_version",
+    "ipn_ctx_launch_count", "ipn_ctx_last_kernel_ms", "ipn_ctx_last_main_kernel_ms", "ipn_ctx_last_loglik_impl", "ipn_ctx_last_rff_impl", "ipn_ctx_last_draw_batch", "ipn_last_error", "ipn_version",
     "ipn_rff_eval", "ipn_rff_eval_dev", "ipn_loglik_delay_grid", "ipn_loglik_delay_grid_dev",
     "ipn_loglik_sky_grid", "ipn_loglik_sky_grid_dev", "ipn_correlate", "ipn_bin_events", "ipn_bin_events_dev", "ipn_thinning_events", "ipn_poisson_counts", "ipn_poisson_counts_dev", "ipn_microbench", "ipn_sky_credible", "ipn_sky_credible_dev",
 )
@@ -77,6 +78,7 @@ def load_library(path: str | None = None):
         lib.ipn_ctx_last_kernel_ms.argtypes = [_p]
         lib.ipn_ctx_last_kernel_ms.restype = C.c_double
         lib.ipn_ctx_last_loglik_impl.argtypes = [_p]
+        lib.ipn_ctx_last_rff_impl.argtypes = [_p]
         lib.ipn_ctx_last_draw_batch.argtypes = [_p]
         lib.ipn_ctx_last_draw_batch.restype = _i64
         lib.ipn_ctx_last_main_kernel_ms.argtypes = [_p, C.POINTER(_i64)]
@@ -182,6 +184,11 @@ class Context:
     @property
     def last_loglik_impl(self) -> int:
         return int(self._lib.ipn_ctx_last_loglik_impl(self._h))
+
+    @property
+    def last_rff_impl(self) -> int:
+        """1 = direct kernel, 2 = tcgen05 contraction on uniform bins (the most recent ``rff_eval`` call)."""
+        return int(self._lib.ipn_ctx_last_rff_impl(self._h))
 
     @property
     def last_draw_batch(self) -> int:

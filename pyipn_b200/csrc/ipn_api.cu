@@ -197,6 +197,7 @@ void ipn_ctx_destroy(ipn_ctx* ctx) {
     ctx->misc.release();
     ctx->tcdraw.release();
     ctx->phitab.release();
+    ctx->rffs.release();
     ctx->dbg.release();
     ctx->perm.release();
     for (auto& s : ctx->io) s.release();
@@ -249,6 +250,10 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
             IPN_REQUIRE(value >= 0 && value <= 3, "IPN_OPT_HIFI must be 0 (auto), 1 (fp64), 2 (fp32) or 3 (compensated fp32)");
             ctx->hifi_mode = (int)value;
             return IPN_OK;
+        case IPN_OPT_RFF_IMPL:
+            IPN_REQUIRE(value >= 0 && value <= 2, "IPN_OPT_RFF_IMPL must be 0 (auto), 1 (direct kernel) or 2 (tcgen05 contraction, uniform bins)");
+            ctx->rff_impl = (int)value;
+            return IPN_OK;
         case IPN_OPT_DRAW_BATCH:
             IPN_REQUIRE(value >= 0, "IPN_OPT_DRAW_BATCH must be >= 0");
             ctx->draw_batch = value;
@@ -262,6 +267,7 @@ int ipn_ctx_set_option(ipn_ctx* ctx, int key, int64_t value) {
 uint64_t ipn_ctx_launch_count(const ipn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double ipn_ctx_last_kernel_ms(const ipn_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 int ipn_ctx_last_loglik_impl(const ipn_ctx* ctx) { return ctx ? ctx->last_impl : 0; }
+int ipn_ctx_last_rff_impl(const ipn_ctx* ctx) { return ctx ? ctx->last_rff_impl : 0; }
 int64_t ipn_ctx_last_draw_batch(const ipn_ctx* ctx) { return ctx ? ctx->last_draw_batch : 0; }
 double ipn_ctx_last_main_kernel_ms(const ipn_ctx* ctx, int64_t* launches) {
     if (!ctx) return 0.0;
@@ -283,6 +289,52 @@ static int check_rff_args(int64_t T, const void* time, int64_t S, int64_t J, con
     return IPN_OK;
 }
 
+// Are the bins uniform (time[i] = time[0] + i dt)?  The tolerance is what float64 arithmetic on np.arange edges leaves (a few
+// ulp of the largest time) -- far below what matters: a deviation d enters the phase as omega d.
+static bool uniform_host(int64_t T, const double* time, double* t0, double* dt) {
+    if (T < 2) return false;
+    *t0 = time[0];
+    *dt = (time[T - 1] - time[0]) / (double)(T - 1);
+    if (!(*dt > 0.0) || !std::isfinite(*dt)) return false;
+    const double tol = 1e-12 * (std::fabs(time[0]) + std::fabs(time[T - 1]));
+    for (int64_t i = 0; i < T; ++i)
+        if (!(std::fabs(time[i] - (*t0 + (double)i * *dt)) <= tol)) return false;
+    return true;
+}
+
+// device arrays; route by IPN_OPT_RFF_IMPL (uniform / t0 / dt already known for the host entry point)
+static int rff_eval_device(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega, const double* a,
+                           const double* b, const double* shift, const double* amp, double* out, int known_uniform, double t0,
+                           double dt) {
+    int rc;
+    bool contraction = false;
+    if (ctx->rff_impl != 1 && rff_tc_supported(T, J)) {
+        if (known_uniform < 0) {  // not known yet: ask the device
+            bool uni = false;
+            if (ctx->rff_impl == 2) {
+                double t2[2];
+                IPN_CUDA_CHECK(cudaMemcpyAsync(&t2[0], time, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                IPN_CUDA_CHECK(cudaMemcpyAsync(&t2[1], time + (T - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+                IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                t0 = t2[0];
+                dt = (t2[1] - t2[0]) / (double)(T - 1);
+                uni = dt > 0.0;
+            } else if ((rc = rff_uniform_dev(ctx, T, time, &t0, &dt, &uni))) {
+                return rc;
+            }
+            known_uniform = uni ? 1 : 0;
+        }
+        contraction = known_uniform == 1;
+    }
+    if (ctx->rff_impl == 2 && !contraction) {
+        set_error("IPN_OPT_RFF_IMPL = 2 needs uniform bins, T >= 1024 and J <= 108 (T = %lld, J = %lld)", (long long)T, (long long)J);
+        return IPN_ERR_UNSUPPORTED;
+    }
+    ctx->last_rff_impl = contraction ? 2 : 1;
+    if (contraction) return run_rff_eval_tc(ctx, T, time, t0, dt, S, J, omega, a, b, shift, amp, out);
+    return launch_rff_eval(ctx, T, time, S, J, omega, a, b, shift, amp, out);
+}
+
 int ipn_rff_eval_dev(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
                      const double* a, const double* b, const double* shift, const double* amp, double* out) {
     int rc = ctx_guard(ctx);
@@ -291,7 +343,7 @@ int ipn_rff_eval_dev(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int
     if (rc) return rc;
     if (T == 0 || S == 0) return IPN_OK;
     begin_timing(ctx);
-    rc = launch_rff_eval(ctx, T, time, S, J, omega, a, b, shift, amp, out);
+    rc = rff_eval_device(ctx, T, time, S, J, omega, a, b, shift, amp, out, -1, 0.0, 0.0);
     end_timing(ctx);
     return rc;
 }
@@ -303,6 +355,8 @@ int ipn_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t
     rc = check_rff_args(T, time, S, J, omega, a, b, shift, amp, out);
     if (rc) return rc;
     if (T == 0 || S == 0) return IPN_OK;
+    double t0 = 0.0, dt = 0.0;
+    const int uni = (ctx->rff_impl != 1 && uniform_host(T, time, &t0, &dt)) ? 1 : 0;
     const size_t sj = (size_t)S * J * sizeof(double);
     if ((rc = h2d(ctx, ctx->io[0], time, (size_t)T * 8))) return rc;
     if ((rc = h2d(ctx, ctx->io[1], omega, sj))) return rc;
@@ -312,9 +366,8 @@ int ipn_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t
     if ((rc = h2d(ctx, ctx->io[5], amp, (size_t)S * 8))) return rc;
     if ((rc = ctx->io[6].ensure((size_t)S * T * 8))) return rc;
     begin_timing(ctx);
-    rc = launch_rff_eval(ctx, T, ctx->io[0].as<double>(), S, J, ctx->io[1].as<double>(), ctx->io[2].as<double>(),
-                         ctx->io[3].as<double>(), ctx->io[4].as<double>(), ctx->io[5].as<double>(),
-                         ctx->io[6].as<double>());
+    rc = rff_eval_device(ctx, T, ctx->io[0].as<double>(), S, J, ctx->io[1].as<double>(), ctx->io[2].as<double>(),
+                         ctx->io[3].as<double>(), ctx->io[4].as<double>(), ctx->io[5].as<double>(), ctx->io[6].as<double>(), uni, t0, dt);
     end_timing(ctx);
     if (rc) return rc;
     IPN_CUDA_CHECK(cudaMemcpyAsync(out, ctx->io[6].p, (size_t)S * T * 8, cudaMemcpyDeviceToHost, ctx->stream));

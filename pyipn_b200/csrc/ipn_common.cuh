@@ -62,6 +62,8 @@ struct ipn_ctx {
     int precise_w = 1;
     int hifi_mode = 0;  // tcgen05 path epilogue: 0 auto, 1 force fp64, 2 force plain fp32, 3 force compensated fp32
     int64_t draw_batch = 0;
+    int rff_impl = 0;   // ipn_rff_eval: 0 auto, 1 direct kernel, 2 tcgen05 contraction (uniform bins guaranteed by the caller)
+    int last_rff_impl = 0;
     int n_terms = 1;    // how many likelihood passes are summed into the caller's result (sky grid: D detectors): the 1e-3 nat
                         // tolerance is shared between them, so the per-draw epilogue choice is made for a 1 / n_terms share
     // scratch
@@ -74,6 +76,7 @@ struct ipn_ctx {
     ipn::Scratch perm;     // bin permutation (counts > 0 first) of the tcgen05 path
     ipn::Scratch dbg;      // pipeline wait counters (IPN_TC_DEBUG)
     ipn::Scratch tcdraw;   // per-draw scale factors of the tcgen05 path
+    ipn::Scratch rffs;     // ipn_rff_eval through the contraction: bin / delay tables, signs, draw constants
     ipn::Scratch phitab;   // 1024-point fixed-point unit circle of the Phi image kernel (built on first use)
     void* pinned = nullptr;  // pinned host bounce buffer
     size_t pinned_cap = 0;
@@ -96,6 +99,12 @@ int launch_poisson_counts(ipn_ctx* ctx, int64_t T, const double* exposure, int64
 int launch_sky_delays(ipn_ctx* ctx, int64_t D, const double* sc_pos, int64_t P, const double* ghat, double* delays);
 
 int run_microbench(ipn_ctx* ctx, int which, double* result);
+
+// ipn_rff_eval on uniform bins through the tcgen05 contraction (loglik_tc.cu); rff_uniform_dev checks time[i] = t0 + i dt on the device
+bool rff_tc_supported(int64_t T, int64_t J);
+int run_rff_eval_tc(ipn_ctx* ctx, int64_t T, const double* time, double t0, double dt, int64_t S, int64_t J, const double* omega,
+                    const double* a, const double* b, const double* shift, const double* amp, double* out);
+int rff_uniform_dev(ipn_ctx* ctx, int64_t T, const double* d_time, double* t0, double* dt, bool* uniform);
 
 int launch_bin_events(ipn_ctx* ctx, int64_t n_events, const double* times, double tstart, double dt, int64_t n_edges,
                       int64_t* counts);

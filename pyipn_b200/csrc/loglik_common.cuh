@@ -29,6 +29,14 @@ struct DrawConst {
     float c_lo;
 };
 
+// per-draw scale and epilogue choice of the tcgen05 path (tc_draw_kernel, tc_images.cuh)
+struct TcDraw {
+    float ks;     // kappa = 2^-12 / sigma
+    float sigma;  // power of two
+    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* in loglik_tc.cu)
+    int pad;
+};
+
 #ifndef IPN_HOST_EMU
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -82,6 +82,18 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
 #endif
 }
 
+// Store epilogue (ipn_rff_eval on uniform bins through the same contraction): no Poisson terms, just u = 2^x of the eight bins.
+__device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                                 float ks, float ks8, float ks24, float mks, float mks8, float (&u)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
+        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
+        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
+        u[j] = exp2_hilo(xh, xl);
+    }
+}
+
 // Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
 // not the exponent or the logarithm but three roundings of O(n)-sized quantities: n*y0, kappa*u and their difference
 // (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of eight such terms.  Here the two products and the

@@ -56,6 +56,11 @@ struct TcParams {
     int64_t G, Gpad;
     uint32_t a_bytes, b_dig, img_bytes, a_plane, b_plane;  // sizes / plane strides in bytes
     const int* flags;         // [0] = #bins with counts, [1] = epilogue mode option, [2..3] = sum n_i^2 (double)
+    // store mode (EPI_STORE): out[sl * out_T + p * out_Q + q] = sgn[sl] 2^x for "bin" p (column) and "delay" q (row), see run_rff_eval_tc
+    double* out;
+    int64_t out_T;
+    int out_Q;
+    const double* sgn;        // [Sb] +1, -1 or 0 (sign of the draw's amplitude)
     // the fields below are only read by a -DIPN_TC_HOOKS build (IPN_HOOK())
     int one_issuer;           // experiment switch (IPN_TC_ONE_ISSUER): warp 13 issues every tile, warp 14 only takes part in the hand-shakes
     int epi_delay;            // test hook (IPN_TC_EPI_DELAY, cycles): stall every epilogue unit -> protocol must survive a slow consumer
@@ -253,7 +258,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8]) {
 // One instantiation per epilogue mode (EPI_FP32 / EPI_COMP / EPI_FP64): each handles only the draws flagged for its mode
 // (every role skips the others' items), so the common fp32 instantiation carries no compensated or fp64 code in its
 // instruction-cache footprint.
-enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, N_EPI = 3 };
+enum { EPI_FP32 = 0, EPI_COMP = 1, EPI_FP64 = 2, N_EPI = 3, EPI_STORE = 3 };  // EPI_STORE: the contraction with a store epilogue (ipn_rff_eval)
 // (register budget: 96 per thread -- 19 warps x 32 x 104 does not launch, the allocation granule is 512 registers per warp)
 template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcParams p) {
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    constexpr int DRAW_MODE = MODE == EPI_STORE ? (int)EPI_FP32 : MODE;  // which draws (TcDraw::hifi) this instantiation works on
     const int items_per_draw = p.nchunk * p.n_dt;
     const int64_t n_items = (int64_t)p.Sb * items_per_draw;
 
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const bool dbg = IPN_HOOK(dbg) != nullptr;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
                 const int sl = (int)(item / items_per_draw);
-                if (p.td[sl].hifi != MODE) {
+                if (p.td[sl].hifi != DRAW_MODE) {
                     --item_seq;  // not this instantiation's draw: the item does not exist for any role
                     continue;
                 }
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = IPN_HOOK(dbg) != nullptr;
         const long long t_start = clock64();
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_seq) {
-            if (p.td[(int)(item / items_per_draw)].hifi != MODE) {
+            if (p.td[(int)(item / items_per_draw)].hifi != DRAW_MODE) {
                 --item_seq;
                 continue;
             }
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
         const bool dbg = IPN_HOOK(dbg) != nullptr;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int sl = (int)(item / items_per_draw);
-            if (p.td[sl].hifi != MODE) continue;
+            if (p.td[sl].hifi != DRAW_MODE) continue;
             const int rem = (int)(item - (int64_t)sl * items_per_draw);
             const int chunk = rem / p.n_dt, dt = rem - chunk * p.n_dt;
             const int bt0 = chunk * p.tiles_per_chunk;
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             double hacc = 0.0;
             const double ksd = (double)ks;
+            const double sgn = MODE == EPI_STORE ? p.sgn[sl] : 0.0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
@@ -599,7 +606,20 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     } else {
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
-                            if (MODE == EPI_FP64)
+                            if (MODE == EPI_STORE) {
+                                float u8[8];
+                                epi_units8_store(acc[h][0], acc[h][1], acc[h][2], acc[h][3], ks, ks8, ks24, mks, mks8, u8);
+                                // bin i = p Q + q: p = the column's position among the "bins", q = this thread's "delay" row;
+                                // for one column the 32 lanes of the warp write 256 consecutive bytes
+                                const int64_t q = (int64_t)dt * TM + quarter * 32 + lane;
+                                const int64_t p0 = (int64_t)bt * TN + cg * GCOLS + 8 * h;
+                                double* orow = p.out + (int64_t)sl * p.out_T;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int64_t i = (p0 + j) * p.out_Q + q;
+                                    if (q < p.out_Q && i < p.out_T) orow[i] = sgn * (double)u8[j];
+                                }
+                            } else if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
                             else if (MODE == EPI_COMP && has_counts)
                                 epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
@@ -615,9 +635,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     if (lane == 0) mbar_arrive(c_empty + cs);
                 }
             }
-            double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
-            const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
-            if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
+            if (MODE != EPI_STORE) {
+                double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
+                const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
+                if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
+            }
         }
         if (dbg && warp == 0 && lane == 0) {
             p.dbg[blockIdx.x * 8 + 5] = w_cf;
@@ -644,9 +666,25 @@ static int ensure_phitab(ipn_ctx* ctx) {
 
 bool tc_supported(int64_t J) { return 2 * J + tc::MIN_CROWS <= tc::KPAD_MAX; }
 
-int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+// Store mode of the runner (ipn_rff_eval on uniform bins, run_rff_eval_tc below): the caller supplies the bin permutation and
+// the flag block (no counts to sort), a delay grid PER DRAW, and instead of reducing over the bins the epilogue stores 2^x.
+struct TcStore {
+    double* out;           // [S][out_T]
+    int64_t out_T;
+    int out_Q;             // bins i = p * out_Q + q ("bin" p, "delay" q)
+    const double* sgn;     // [S]
+    const int* perm;       // [T] identity
+    const int* flags;      // [8]: n_nz = 0, mode option 2 (plain fp32 unless the exponent is unbounded), sum n^2 = 0
+    const double *time, *shift, *amp;  // the caller's arrays, for the draws the direct kernel has to take (unbounded exponent)
+};
+
+int launch_rff_eval_masked(ipn_ctx* ctx, int64_t T, const double* time, int64_t S0, int64_t Sb, int64_t J, const double* omega,
+                           const double* a, const double* b, const double* shift, const double* amp, double* out,
+                           const void* tcdraw);  // rff_eval.cu: draws S0 .. S0 + Sb - 1 with TcDraw::hifi == 2 only
+
+static int run_tc_grid(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
                        int64_t S, int64_t J, const double* omega, const double* a, const double* b, const DrawConst* d_dc,
-                       int64_t G, const double* delays, double* ll, bool accumulate) {
+                       int64_t G, const double* delays, int64_t delay_stride, double* ll, bool accumulate, const TcStore* st) {
     using namespace tc;
     if (!tc_supported(J)) {
         set_error("tcgen05 path supports J <= %d (got %lld)", (KPAD_MAX - MIN_CROWS) / 2, (long long)J);
@@ -675,31 +713,41 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     int rc;
     if ((rc = ctx->wtab.ensure((size_t)Sbatch * w_per_draw))) return rc;
     if ((rc = ctx->misc.ensure((size_t)Sbatch * p_per_draw))) return rc;
-    if ((rc = ctx->accum.ensure((size_t)Sbatch * Gpad * sizeof(double)))) return rc;
+    if (!st && (rc = ctx->accum.ensure((size_t)Sbatch * Gpad * sizeof(double)))) return rc;
     if ((rc = ctx->tcdraw.ensure((size_t)Sbatch * sizeof(TcDraw)))) return rc;
-    const int n_pblk = (int)((T + 1023) / 1024);
-    const size_t perm_ints = (((size_t)T + 8 + 1) / 2) * 2;  // flags + permutation, padded so the doubles behind stay aligned
-    if ((rc = ctx->perm.ensure(perm_ints * sizeof(int) + (size_t)(n_pblk + 1) * (sizeof(double) + 4 * sizeof(int)) + 64))) return rc;
-    int* d_nnz = ctx->perm.as<int>();  // [0] n_nz, [1] mode, [2..3] sum n^2 as double (8-byte aligned)
-    int* d_perm = d_nnz + 8;
-    double* d_blk_sq = reinterpret_cast<double*>(d_nnz + perm_ints);
-    int* d_blk_cnt = reinterpret_cast<int*>(d_blk_sq + n_pblk + 1);
-    if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
-    tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, d_perm, d_nnz,
-                                                                    ctx->hifi_mode);  // T == 0: only writes the flags
-    ctx->launches += n_pblk > 0 ? 2 : 1;
+    const int* d_nnz;   // [0] n_nz, [1] mode, [2..3] sum n^2 as double (8-byte aligned)
+    const int* d_perm;
+    if (st) {
+        d_nnz = st->flags;
+        d_perm = st->perm;
+    } else {
+        const int n_pblk = (int)((T + 1023) / 1024);
+        const size_t perm_ints = (((size_t)T + 8 + 1) / 2) * 2;  // flags + permutation, padded so the doubles behind stay aligned
+        if ((rc = ctx->perm.ensure(perm_ints * sizeof(int) + (size_t)(n_pblk + 1) * (sizeof(double) + 4 * sizeof(int)) + 64))) return rc;
+        int* nnz = ctx->perm.as<int>();
+        int* perm = nnz + 8;
+        double* d_blk_sq = reinterpret_cast<double*>(nnz + perm_ints);
+        int* d_blk_cnt = reinterpret_cast<int*>(d_blk_sq + n_pblk + 1);
+        if (n_pblk > 0) tc_perm_count_kernel<<<n_pblk, 1024, 0, ctx->stream>>>(T, counts, d_blk_cnt, d_blk_sq);
+        tc_perm_kernel<<<n_pblk > 0 ? n_pblk : 1, 1024, 0, ctx->stream>>>(T, counts, n_pblk, d_blk_cnt, d_blk_sq, perm, nnz,
+                                                                        ctx->hifi_mode);  // T == 0: only writes the flags
+        ctx->launches += n_pblk > 0 ? 2 : 1;
+        d_nnz = nnz;
+        d_perm = perm;
+    }
     uint8_t* d_W = ctx->wtab.as<uint8_t>();
     uint8_t* d_P = ctx->misc.as<uint8_t>();
     double* d_R = ctx->accum.as<double>();
     TcDraw* d_td = ctx->tcdraw.as<TcDraw>();
 
-    void (*kern[N_EPI])(const TcParams) = {nullptr, nullptr, nullptr};  // by epilogue mode
+    void (*kern[N_EPI + 1])(const TcParams) = {nullptr, nullptr, nullptr, nullptr};  // by epilogue mode
     switch (ksteps) {
 #define IPN_TC_CASE(K)                            \
     case K:                                       \
         kern[0] = loglik_tc_kernel<K, EPI_FP32>;  \
         kern[1] = loglik_tc_kernel<K, EPI_COMP>;  \
         kern[2] = loglik_tc_kernel<K, EPI_FP64>;  \
+        kern[3] = loglik_tc_kernel<K, EPI_STORE>; \
         break;
         IPN_TC_CASE(1) IPN_TC_CASE(2) IPN_TC_CASE(3) IPN_TC_CASE(4) IPN_TC_CASE(5) IPN_TC_CASE(6)
         default: IPN_TC_CASE(7)
@@ -708,20 +756,20 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
     // which instantiations can have work: auto -> fp32, compensated and (rarely) fp64; forced modes -> one
     // (a draw whose exponent is not bounded goes to the fp64 epilogue whatever the option says, so that one always runs)
     const int hm = ctx->hifi_mode;
-    const bool run_mode[N_EPI] = {hm == 0 || hm == 2, hm == 0 || hm == 3, true};
+    const bool run_mode[N_EPI + 1] = {!st && (hm == 0 || hm == 2), !st && (hm == 0 || hm == 3), !st, st != nullptr};
     {
         int* trap = trap_record_device_ptr();
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int m = 0; m < N_EPI; ++m)
+    for (int m = 0; m <= N_EPI; ++m)
         if (run_mode[m]) IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
-        IPN_CUDA_CHECK(cudaMemsetAsync(d_R, 0, (size_t)Sb * Gpad * sizeof(double), ctx->stream));
+        if (!st) IPN_CUDA_CHECK(cudaMemsetAsync(d_R, 0, (size_t)Sb * Gpad * sizeof(double), ctx->stream));
         tc_draw_kernel<<<(Sb + 127) / 128, 128, 0, ctx->stream>>>(S0, Sb, (int)J, Kpad - 2 * (int)J, a, b, d_dc, d_nnz, ctx->n_terms, d_td);
         tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
-                                                                            n_dt, a_bytes, a_plane, d_W);
+                                                                            delay_stride, n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
             tc_pimg_kernel<<<dim3(n_bt, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
                                                                      omega, d_dc, d_td, ctx->phitab.as<PhiTabEntry>(), n_bt, b_bytes, b_plane, d_P);
@@ -756,6 +804,10 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
             const int64_t items = (int64_t)Sb * nchunk * n_dt;
             int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
             p.flags = d_nnz;
+            p.out = st ? st->out + S0 * st->out_T : nullptr;
+            p.out_T = st ? st->out_T : 0;
+            p.out_Q = st ? st->out_Q : 0;
+            p.sgn = st ? st->sgn + S0 : nullptr;
             p.skip_math = p.skip_mma = p.epi_delay = p.one_issuer = 0;
             p.dbg = nullptr;
             bool want_dbg = false;
@@ -773,7 +825,7 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                 p.dbg = ctx->dbg.as<unsigned long long>();
             }
             main_kernel_begin(ctx);
-            for (int m = 0; m < N_EPI; ++m) {
+            for (int m = 0; m <= N_EPI; ++m) {
                 if (!run_mode[m]) continue;
                 // the per-draw modes are decided on the device, so in auto mode all three are launched; an instantiation
                 // without draws of its mode exits at once (~15 us)
@@ -797,10 +849,95 @@ int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double
                         m[5] / tiles, m[6] / tiles);
             }
         }
-        rc = finalize_loglik(ctx, S0, Sb, S, G, Gpad, d_R, d_dc, ll, accumulate);
-        if (rc) return rc;
+        if (!st) {
+            rc = finalize_loglik(ctx, S0, Sb, S, G, Gpad, d_R, d_dc, ll, accumulate);
+            if (rc) return rc;
+        } else {
+            // draws of this batch with an unbounded exponent (TcDraw::hifi == 2): the direct kernel, those draws only
+            rc = launch_rff_eval_masked(ctx, st->out_T, st->time, S0, Sb, J, omega, a, b, st->shift, st->amp, st->out, d_td);
+            if (rc) return rc;
+        }
     }
     return IPN_OK;
+}
+
+int run_loglik_grid_tc(ipn_ctx* ctx, int64_t T, const double* time, const double* exposure, const int64_t* counts,
+                       int64_t S, int64_t J, const double* omega, const double* a, const double* b, const DrawConst* d_dc,
+                       int64_t G, const double* delays, double* ll, bool accumulate) {
+    return run_tc_grid(ctx, T, time, exposure, counts, S, J, omega, a, b, d_dc, G, delays, 0, ll, accumulate, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// ipn_rff_eval on UNIFORM bins (the only way the reference calls it: mid-points of np.arange edges) as the same contraction.
+// With Q = 128 and bin i = p Q + q the argument splits into  t_i - shift_s = (t_0 + p Q dt) - (shift_s - q dt)  -- a "bin"
+// time t'_p = t_0 + p Q dt (T / Q of them) and a per-draw "delay" grid D_sq = shift_s - q dt (Q of them) -- so the
+// log-intensity of every bin of a draw is ONE (T / Q x 2J) . (2J x Q) product:  log2 lambda[p, q] = log2|amp| + sum_k Phi[p, k]
+// W[k, q]: (T / Q + Q) J sine / cosine pairs per draw instead of T J, 2J multiply-adds per (draw, bin) on the tensor pipe
+// instead of ~4300 FP32-pipe instructions, and the digit-plane arithmetic keeps the exponent exact to ~1e-9, so
+// lambda = 2^x carries only the 7e-8 of the fp32 exp2 (tolerance: 1e-6 relative).  One work item = one draw (T / Q / 32 tiles
+// of the kernel above with the store epilogue).  Draws whose exponent is not bounded by 2^120 (tc_draw_kernel) are left to
+// the direct kernel (rff_eval.cu), which handles overflow to inf as the reference does.
+// ------------------------------------------------------------------------------------------------------
+constexpr int RFF_Q = 128;
+
+__global__ void rff_tc_bins_kernel(int64_t Tp, double t0, double step, double* __restrict__ time_p, double* __restrict__ expo_p,
+                                   int64_t* __restrict__ counts_p, int* __restrict__ perm, int* __restrict__ flags) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < Tp) {
+        time_p[p] = t0 + (double)p * step;
+        expo_p[p] = 0.0;
+        counts_p[p] = 0;
+        perm[p] = (int)p;
+    }
+    if (p == 0) {
+        flags[0] = 0;  // no bin holds counts: the tiles' constants are not used
+        flags[1] = 2;  // IPN_OPT_HIFI = 2: TcDraw::hifi = 0 unless the draw's exponent is unbounded (then 2)
+        flags[2] = flags[3] = 0;  // sum n^2 = 0.0
+    }
+}
+
+__global__ void rff_tc_draws_kernel(int64_t S, double dt, const double* __restrict__ shift, const double* __restrict__ amp,
+                                    double* __restrict__ delays, double* __restrict__ sgn, DrawConst* __restrict__ dc) {
+    const int64_t s = blockIdx.x;
+    for (int q = threadIdx.x; q < RFF_Q; q += blockDim.x) delays[s * RFF_Q + q] = shift[s] - (double)q * dt;
+    if (threadIdx.x == 0) {
+        const double am = amp[s];
+        sgn[s] = am > 0.0 ? 1.0 : (am < 0.0 ? -1.0 : 0.0);
+        DrawConst d;
+        d.C = 0.0;
+        d.kap = 0.0;
+        const double c = am != 0.0 ? log2(fabs(am)) : 0.0;  // amp = 0: x = log2 f, multiplied by sgn = 0 at the store
+        d.c_hi = (float)c;
+        d.c_lo = (float)(c - (double)d.c_hi);
+        dc[s] = d;
+    }
+}
+
+bool rff_tc_supported(int64_t T, int64_t J) { return tc_supported(J) && T >= 8 * RFF_Q; }
+
+// time[i] = t0 + i dt (checked by the caller), all arrays on the device
+int run_rff_eval_tc(ipn_ctx* ctx, int64_t T, const double* time, double t0, double dt, int64_t S, int64_t J, const double* omega,
+                    const double* a, const double* b, const double* shift, const double* amp, double* out) {
+    const int64_t Tp = (T + RFF_Q - 1) / RFF_Q;
+    // scratch: time' | exposure' | counts' (Tp each) | delays (S x Q) | sgn (S) | DrawConst (S) | flags (8) | perm (Tp)
+    const size_t n8 = (size_t)3 * Tp + (size_t)S * RFF_Q + (size_t)S;
+    const size_t bytes = n8 * 8 + (size_t)S * sizeof(DrawConst) + 8 * sizeof(int) + (size_t)Tp * sizeof(int) + 64;
+    int rc = ctx->rffs.ensure(bytes);
+    if (rc) return rc;
+    double* time_p = ctx->rffs.as<double>();
+    double* expo_p = time_p + Tp;
+    int64_t* counts_p = reinterpret_cast<int64_t*>(expo_p + Tp);
+    double* delays = reinterpret_cast<double*>(counts_p + Tp);
+    double* sgn = delays + (size_t)S * RFF_Q;
+    DrawConst* dc = reinterpret_cast<DrawConst*>(sgn + S);
+    int* flags = reinterpret_cast<int*>(dc + S);
+    int* perm = flags + 8;
+    rff_tc_bins_kernel<<<(unsigned)((Tp + 255) / 256), 256, 0, ctx->stream>>>(Tp, t0, (double)RFF_Q * dt, time_p, expo_p, counts_p, perm, flags);
+    rff_tc_draws_kernel<<<(unsigned)S, 128, 0, ctx->stream>>>(S, dt, shift, amp, delays, sgn, dc);
+    ctx->launches += 2;
+    IPN_CUDA_CHECK(cudaGetLastError());
+    TcStore st{out, T, RFF_Q, sgn, perm, flags, time, shift, amp};
+    return run_tc_grid(ctx, Tp, time_p, expo_p, counts_p, S, J, omega, a, b, dc, RFF_Q, delays, RFF_Q, nullptr, false, &st);
 }
 
 }  // namespace ipn

@@ -23,9 +23,10 @@ constexpr int RFF_TILE = RFF_THREADS * RFF_BINS_PER_THREAD;
 
 template <bool kFullFp64>
 __global__ void __launch_bounds__(RFF_THREADS)
-rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, const double* __restrict__ omega,
+rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S0, int64_t S, int J, const double* __restrict__ omega,
                 const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ shift,
-                const double* __restrict__ amp, double* __restrict__ out, int64_t tiles_per_draw) {
+                const double* __restrict__ amp, double* __restrict__ out, int64_t tiles_per_draw,
+                const TcDraw* __restrict__ only) {
     // the float4 table comes first: behind 3 J doubles it would sit at 8 mod 16 bytes for odd J (misaligned LDS.128)
     extern __shared__ __align__(16) unsigned char sm_raw[];
     float4* s_f = reinterpret_cast<float4*>(sm_raw);      // [J] (wh, wl, a, b) with w in turns per unit time
@@ -37,8 +38,11 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
     const int64_t n_items = S * tiles_per_draw;
     int64_t cur_s = -1;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int64_t s = item / tiles_per_draw;
-        const int64_t tile = item - s * tiles_per_draw;
+        const int64_t sl = item / tiles_per_draw;
+        const int64_t s = S0 + sl;  // draws S0 .. S0 + S - 1
+        const int64_t tile = item - sl * tiles_per_draw;
+        // masked run behind the contraction route (loglik_tc.cu: run_rff_eval_tc): only the draws it left out
+        if (only && only[sl].hifi != 2) continue;
         if (s != cur_s) {
             __syncthreads();
             if (threadIdx.x == 0) s_wmax = 0u;
@@ -146,10 +150,49 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S, int J, co
     }
 }
 
-int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
-                    const double* a, const double* b, const double* shift, const double* amp, double* out) {
+// max_i |time[i] - (time[0] + i dt)| with dt = (time[T - 1] - time[0]) / (T - 1): are the bins uniform?  (atomicMax on the bit
+// pattern of a non-negative double)
+__global__ void __launch_bounds__(256) rff_uniform_kernel(int64_t T, const double* __restrict__ time, double* __restrict__ res) {
+    const double t0 = time[0], tl = time[T - 1];
+    const double dt = (tl - t0) / (double)(T - 1);
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x) {
+        const double d = fabs(time[i] - (t0 + (double)i * dt));
+        m = (d > m || d != d) ? (d != d ? __longlong_as_double(0x7ff0000000000000ll) : d) : m;  // NaN -> inf
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(res + 2), (unsigned long long)__double_as_longlong(m));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        res[0] = t0;
+        res[1] = tl;
+    }
+}
+
+int rff_uniform_dev(ipn_ctx* ctx, int64_t T, const double* d_time, double* t0, double* dt, bool* uniform) {
+    *uniform = false;
+    if (T < 2) return IPN_OK;
+    int rc = ctx->rffs.ensure(64);
+    if (rc) return rc;
+    double* res = ctx->rffs.as<double>();
+    IPN_CUDA_CHECK(cudaMemsetAsync(res, 0, 24, ctx->stream));
+    const int grid = (int)std::min<int64_t>((T + 255) / 256, (int64_t)ctx->sm_count * 4);
+    rff_uniform_kernel<<<grid, 256, 0, ctx->stream>>>(T, d_time, res);
+    ctx->launches += 1;
+    double h[3];
+    IPN_CUDA_CHECK(cudaMemcpyAsync(h, res, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    IPN_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *t0 = h[0];
+    *dt = (h[1] - h[0]) / (double)(T - 1);
+    *uniform = *dt > 0.0 && std::isfinite(*dt) && h[2] <= 1e-12 * (std::fabs(h[0]) + std::fabs(h[1]));
+    return IPN_OK;
+}
+
+// draws S0 .. S0 + Sb - 1; tcdraw != nullptr: only those with TcDraw::hifi == 2 (the contraction route has done the others)
+int launch_rff_eval_masked(ipn_ctx* ctx, int64_t T, const double* time, int64_t S0, int64_t Sb, int64_t J, const double* omega,
+                           const double* a, const double* b, const double* shift, const double* amp, double* out,
+                           const void* tcdraw) {
     const int64_t tiles = (T + RFF_TILE - 1) / RFF_TILE;
-    const int64_t items = S * tiles;
+    const int64_t items = Sb * tiles;
     if (items == 0) return IPN_OK;
     const int64_t max_grid = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(items < max_grid ? items : max_grid);
@@ -158,15 +201,19 @@ int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int6
 #ifdef IPN_TC_HOOKS
     full64 = getenv("IPN_RFF_FP64") != nullptr;  // hooks build only: every draw through the fp64 side path
 #endif
+    const TcDraw* only = static_cast<const TcDraw*>(tcdraw);
     if (full64)
-        rff_eval_kernel<true><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S, (int)J, omega, a, b, shift, amp,
-                                                                         out, tiles);
+        rff_eval_kernel<true><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S0, Sb, (int)J, omega, a, b, shift, amp, out, tiles, only);
     else
-        rff_eval_kernel<false><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S, (int)J, omega, a, b, shift, amp,
-                                                                          out, tiles);
+        rff_eval_kernel<false><<<grid, RFF_THREADS, smem, ctx->stream>>>(T, time, S0, Sb, (int)J, omega, a, b, shift, amp, out, tiles, only);
     ctx->launches += 1;
     IPN_CUDA_CHECK(cudaGetLastError());
     return IPN_OK;
+}
+
+int launch_rff_eval(ipn_ctx* ctx, int64_t T, const double* time, int64_t S, int64_t J, const double* omega,
+                    const double* a, const double* b, const double* shift, const double* amp, double* out) {
+    return launch_rff_eval_masked(ctx, T, time, 0, S, J, omega, a, b, shift, amp, out, nullptr);
 }
 
 }  // namespace ipn

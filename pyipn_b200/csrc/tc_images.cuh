@@ -67,12 +67,7 @@ constexpr int L6_COL0 = 224;               // the single-buffered level-6 accumu
 static_assert(L6_COL0 + TN <= ACC_COL0 && PWT * (KPAD_MAX / 4) <= L6_COL0, "tensor-memory map");
 }  // namespace tc
 
-struct TcDraw {
-    float ks;     // kappa = 2^-12 / sigma
-    float sigma;  // power of two
-    int hifi;     // epilogue mode of this draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* in loglik_tc.cu)
-    int pad;
-};
+// struct TcDraw: loglik_common.cuh
 
 // ------------------------------------------------------------------------------------------------------
 // operand images (global memory, exactly the shared-memory byte order the UMMA descriptors expect:
@@ -126,8 +121,8 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
 __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpad, const double* __restrict__ omega,
                                                       const double* __restrict__ a, const double* __restrict__ b,
                                                       const DrawConst* __restrict__ dc, const TcDraw* __restrict__ td,
-                                                      int64_t G, const double* __restrict__ delays, int n_dt,
-                                                      uint32_t a_bytes, uint32_t a_plane, uint8_t* __restrict__ Wimg) {
+                                                      int64_t G, const double* __restrict__ delays, int64_t delay_stride,
+                                                      int n_dt, uint32_t a_bytes, uint32_t a_plane, uint8_t* __restrict__ Wimg) {
     const int row = threadIdx.x;  // 0..127
     const int kc = blockIdx.x;    // K chunk of 16
     const int dt = blockIdx.y;
@@ -138,7 +133,7 @@ __global__ void __launch_bounds__(128) tc_wimg_kernel(int64_t S0, int J, int Kpa
     const double cs = (double)dc[s].c_hi + (double)dc[s].c_lo;
     const int ncrow = Kpad - 2 * J;
     alignas(16) int8_t d[tc::PW][16];
-    const double dl = (g < G) ? delays[g] : 0.0;
+    const double dl = (g < G) ? delays[s * delay_stride + g] : 0.0;  // delay_stride = 0: one grid for all draws, G: one per draw
     for (int kk = 0; kk < 16; kk += 2) {
         const int k = kc * 16 + kk;
         long long q0 = 0, q1 = 0;

@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     uint8_t* Wp = W.data() + ((16 - (uintptr_t)W.data() % 16) % 16);  // 16-byte aligned like device allocations
     uint8_t* Pp = P.data() + ((16 - (uintptr_t)P.data() % 16) % 16);
     shim::launch3(tc_wimg_kernel, Dim3{(unsigned)Kpad / 16, (unsigned)n_dt, 1}, 128, (int64_t)0, (int)J, Kpad, omega.data(), a.data(),
-                  b.data(), &dc, &td, G, delays.data(), n_dt, a_bytes, a_plane, Wp);
+                  b.data(), &dc, &td, G, delays.data(), (int64_t)0, n_dt, a_bytes, a_plane, Wp);
     std::vector<PhiTabEntry> phitab(kPhiTabSize);
     shim::launch(tc_phitab_kernel, kPhiTabSize / 256, 256, phitab.data());
     if (n_bt > 0)

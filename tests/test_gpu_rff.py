@@ -109,3 +109,76 @@ def test_argument_errors(ctx):
         ctx.rff_eval(np.arange(4.0), np.ones((1, 600)), np.ones((1, 600)), np.ones((1, 600)), [0.0], [1.0])  # J > IPN_MAX_J
     with pytest.raises(ValueError):
         ctx.rff_eval(np.arange(4.0), np.ones((2, 4)), np.ones((1, 4)), np.ones((2, 4)), [0.0, 0.0], [1.0, 1.0])
+
+
+@pytest.mark.parametrize("T,S,k,scale", [(1024, 2, 50, 0.15), (100_000, 5, 50, 0.15), (4321, 3, 7, 0.45), (20_000, 4, 50, 1.5),
+                                         (99_999, 2, 54, 0.2)])
+def test_rff_eval_uniform_bins_take_the_contraction(ctx, T, S, k, scale):
+    """Bin mid-points of np.arange edges (the only way the reference calls RFF: lightcurve.py:24-47 -> universe.py:441-529):
+    ipn_rff_eval routes to the tcgen05 contraction (bin i = 128 p + q, one (T/128 x 2J).(2J x 128) product per draw, store
+    epilogue).  Same tolerance, 1e-6 relative on lambda; per-draw shifts, negative and zero amplitudes, T not a multiple of
+    128 or 32, large amplitudes (scale 1.5: the exponent bound 2^120 does not hold -> those draws fall to the direct kernel),
+    and the forced direct kernel on the same inputs."""
+    from pyipn_b200._lib import OPT_RFF_IMPL
+
+    rng = np.random.default_rng(T + S + k)
+    edges = -10.0 + 1e-3 * np.arange(T + 1)
+    time = edges[:-1] + 0.5e-3
+    J = 2 * k
+    omega = rng.normal(size=(S, J)) * np.where(np.arange(J) < k, 0.01, 1.0)
+    a = rng.normal(size=(S, J)) * scale
+    b = rng.normal(size=(S, J)) * scale
+    shift = rng.normal(0, 1.0, S)
+    amp = np.exp(rng.normal(size=S))
+    amp[0] = -amp[0]
+    if S > 2:
+        amp[2] = 0.0
+    got = ctx.rff_eval(time, omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == 2
+    for s in range(S):
+        logf = orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])
+        keep = np.abs(logf) < 600.0
+        np.testing.assert_allclose(got[s][keep], amp[s] * np.exp(logf[keep]), rtol=RTOL)
+        if amp[s] == 0.0:
+            assert np.all(got[s] == 0.0)
+    ctx.set_option(OPT_RFF_IMPL, 1)
+    try:
+        direct = ctx.rff_eval(time, omega, a, b, shift, amp)
+        assert ctx.last_rff_impl == 1
+    finally:
+        ctx.set_option(OPT_RFF_IMPL, 0)
+    keep = np.isfinite(direct) & np.isfinite(got)
+    np.testing.assert_allclose(got[keep], direct[keep], rtol=2 * RTOL)
+    assert np.array_equal(np.isfinite(direct), np.isfinite(got))
+
+
+def test_rff_eval_route_follows_the_bins(ctx):
+    """Non-uniform bins, short light curves and J > 108 keep the direct kernel; the device-pointer entry point finds out on
+    the device (one 24-byte read-back) and gives the same numbers as the host entry point."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    T, S, J = 5000, 3, 100
+    time = 2.0 + 0.01 * (np.arange(T) + 0.5)
+    omega = rng.normal(size=(S, J))
+    a = rng.normal(size=(S, J)) * 0.1
+    b = rng.normal(size=(S, J)) * 0.1
+    shift, amp = rng.normal(size=S), np.exp(rng.normal(size=S))
+    ref = ctx.rff_eval(time, omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == 2
+    jig = time.copy()
+    jig[1234] += 1e-7
+    ctx.rff_eval(jig, omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == 1
+    ctx.rff_eval(time[:500], omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == 1
+    ctx.rff_eval(time, np.ones((1, 240)), np.zeros((1, 240)), np.zeros((1, 240)), [0.0], [1.0])
+    assert ctx.last_rff_impl == 1
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(time=time, omega=omega, a=a, b=b, shift=shift, amp=amp).items()}
+    out = torch.empty((S, T), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.rff_eval_dev(T, dev["time"].data_ptr(), S, J, dev["omega"].data_ptr(), dev["a"].data_ptr(), dev["b"].data_ptr(),
+                     dev["shift"].data_ptr(), dev["amp"].data_ptr(), out.data_ptr())
+    ctx.synchronize()
+    assert ctx.last_rff_impl == 2
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
