@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "rff_eval", "config2", "config4", "config5"],
+                    help="config3 (default) is the headline metric; the others are secondary lines of the same shape (see WORKLOADS)")
+    ap.add_argument("--grbs", type=int, default=200, help="config5: GRBs in the population (BASELINE: 1000), sharded over the ranks")
+    ap.add_argument("--nside", type=int, default=64, help="config4: HEALPix resolution (49152 directions at 64)")
     ap.add_argument("--draws", type=int, default=4000, help="total posterior draws, sharded over the ranks (strong scaling)")
     ap.add_argument("--draws-per-gpu", type=int, default=0, help="> 0: fixed work per rank instead (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="the host-buffer end-to-end loop runs min(steps, this) steps")
@@ -180,6 +184,324 @@ def parity_check(a, w, full, S_total, world, batch):
             "seconds": time.perf_counter() - t0}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# secondary workloads (python bench.py --workload ...): the other BASELINE configs and ipn_rff_eval, same line format
+# ---------------------------------------------------------------------------------------------------------------------
+def _wl_rff_eval(a, rank, world, dev, ctx, torch):
+    """a1-a5: 1e5 uniform bins x draws, drop-in for _expeced_rate_multiscale (fit.py:671-691).  Draws sharded over the ranks."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import shard_bounds
+    from pyipn_b200.synth import delay_grid_workload
+
+    S_total = min(a.draws, 1000) if a.draws == 4000 else a.draws  # default 1000 draws: 0.8 GB of float64 output per step
+    w = delay_grid_workload(T=a.bins, G=8, S=S_total, k=a.k)
+    lo, hi = shard_bounds(S_total, rank, world)
+    S, T, J = hi - lo, a.bins, 2 * a.k
+    shift = np.full(S_total, w["true_delay"])
+    host = dict(time=w["time"], omega=w["omega"][lo:hi], a=w["a"][lo:hi], b=w["b"][lo:hi], shift=shift[lo:hi], amp=w["amp"][lo:hi])
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}
+    out = torch.empty((S, T), dtype=torch.float64, device=dev)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in host.items()}
+    res = {}
+
+    def resident():
+        ctx.rff_eval_dev(T, d["time"].data_ptr(), S, J, d["omega"].data_ptr(), d["a"].data_ptr(), d["b"].data_ptr(),
+                         d["shift"].data_ptr(), d["amp"].data_ptr(), out.data_ptr())
+
+    def e2e():
+        res["e2e"] = ctx.rff_eval(pin["time"], pin["omega"], pin["a"], pin["b"], pin["shift"], pin["amp"])
+
+    def parity():
+        got = out.cpu().numpy()
+        pick = sorted({0, S - 1, S // 2, S // 3})
+        r = w["ref"]
+        exp = corc.expected_rate(w["time"], r["omega1"][:, lo:hi][:, pick], r["omega2"][:, lo:hi][:, pick], r["beta1"][:, lo:hi][:, pick],
+                                 r["beta2"][:, lo:hi][:, pick], np.ones(len(pick)), r["scale"][:, lo:hi][:, pick], w["amp"][lo:hi][pick],
+                                 shift[lo:hi][pick])
+        rel = float(np.abs(got[pick] / exp - 1.0).max())
+        same = bool(np.allclose(res["e2e"], got, rtol=1e-12, atol=0)) if "e2e" in res else None
+        return {"checker": "oracle/ipn_oracle.c: _expeced_rate_multiscale (fit.py:671-691) around RFF_multiscale (rff.py:19-29)",
+                "draws_checked": len(pick), "bins": T, "max_rel": rel, "tol": 1e-6, "ok": bool(rel < 1e-6), "e2e_equals_resident": same}
+
+    return dict(name=f"ipn_rff_eval: {S_total} draws x {T} uniform bins of 1 ms, K={a.k} (J={J}); {world} rank(s), draws sharded",
+                metric="RFF intensity draw*bins/s", unit="draw*bins/s", units_step=float(S_total) * T, resident=resident, e2e=e2e,
+                parity=parity, h2d=sum(v.nbytes for v in pin.values()) * world, d2h=S_total * T * 8,
+                roof=dict(bound="hbm", unit="GB/s", bytes_per_unit=8.0, note="algorithmic traffic: one float64 written per (draw, bin); inputs are "
+                          "MB-sized.  achieved = bytes / device time of the whole call (operand images + contraction + store)"),
+                dtype="int8 digit planes -> int32 (exact) + f32 exp2, f64 phases, f64 output", impl=lambda: {"rff_impl": ctx.last_rff_impl})
+
+
+def _wl_config2(a, rank, world, dev, ctx, torch):
+    """2-detector delay grid: 4096 delays x 1e5 bins, ONE draw (latency case).  N > 1: delays sharded."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import gather_rows, shard_bounds
+    from pyipn_b200.synth import delay_grid_workload
+
+    w = delay_grid_workload(T=a.bins, G=a.delays, S=1, k=a.k)
+    lo, hi = shard_bounds(a.delays, rank, world)
+    G, T, J = hi - lo, a.bins, 2 * a.k
+    host = dict(time=w["time"], exposure=w["exposure"], counts=w["counts"], omega=w["omega"], a=w["a"], b=w["b"], amp=w["amp"],
+                bkg=w["bkg"], delays=w["delays"][lo:hi])
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}
+    ll = torch.empty((G, 1), dtype=torch.float64, device=dev)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in host.items()}
+    res = {}
+
+    def resident():
+        ctx.loglik_delay_grid_dev(T, d["time"].data_ptr(), d["exposure"].data_ptr(), d["counts"].data_ptr(), 1, J, d["omega"].data_ptr(),
+                                  d["a"].data_ptr(), d["b"].data_ptr(), d["amp"].data_ptr(), d["bkg"].data_ptr(), G, d["delays"].data_ptr(),
+                                  ll.data_ptr())
+        res["full"] = gather_rows(ll, a.delays) if world > 1 else ll
+
+    def e2e():
+        r = ctx.loglik_delay_grid(pin["time"], pin["exposure"], pin["counts"], pin["omega"], pin["a"], pin["b"], pin["amp"], pin["bkg"], pin["delays"])
+        if world > 1:
+            gather_rows(torch.from_numpy(r).to(dev), a.delays)
+
+    def parity():
+        full = res["full"].cpu().numpy()[:, 0]
+        best = int(np.argmax(full))
+        idx = np.unique(np.concatenate([np.arange(max(0, best - 3), min(a.delays, best + 4)), np.arange(0, a.delays, max(1, a.delays // 40))]))
+        exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"][idx])[:, 0]
+        err = float(np.abs(full[idx] - exp).max())
+        return {"checker": "oracle/ipn_oracle.c", "delays_checked": int(idx.size), "max_abs_nats": err, "tol": 1e-3,
+                "argmax_equal": bool(idx[int(np.argmax(exp))] == best), "argmax_index": best,
+                "gap_to_second_best_nats": float(np.sort(exp)[-1] - np.sort(exp)[-2]), "ok": bool(err < 1e-3 and idx[int(np.argmax(exp))] == best)}
+
+    return dict(name=f"config2 delay grid: {a.delays} delays x 1 draw x {T} bins, K={a.k}; {world} rank(s), delays sharded",
+                metric="RFF Poisson loglik grid-points*bins/s", unit="grid-point*bins/s", units_step=float(a.delays) * T, resident=resident, e2e=e2e,
+                parity=parity, h2d=sum(v.nbytes for v in pin.values()) * world, d2h=a.delays * 8, roof=None,
+                dtype="int8 digit planes -> int32 (exact) + f32 epilogue", impl=lambda: {"loglik_impl": ctx.last_loglik_impl})
+
+
+def _wl_config4(a, rank, world, dev, ctx, torch):
+    """8-detector sky grid: HEALPix nside 64 (49152 directions) x 8 detectors x 1e5 bins, one draw.  N > 1: directions sharded, all
+    detectors on every rank (the detector sum stays local), one all-gather of the per-direction sums."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import gather_rows, shard_bounds
+    from pyipn_b200.synth import sky_grid_workload
+
+    w = sky_grid_workload(D=8, T=a.bins, S=1, nside=a.nside, k=a.k)
+    P_total = w["ghat"].shape[0]
+    lo, hi = shard_bounds(P_total, rank, world)
+    P, T, J, D = hi - lo, a.bins, 2 * a.k, 8
+    host = dict(time=w["time"], exposure=w["exposure"], counts=w["counts"], sc_pos=w["sc_pos"], ghat=w["ghat"][lo:hi], omega=w["omega"],
+                a=w["a"], b=w["b"], amp=w["amp"], bkg=w["bkg"])
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}
+    ll = torch.empty((P, 1), dtype=torch.float64, device=dev)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in host.items()}
+    res = {}
+
+    def resident():
+        ctx.loglik_sky_grid_dev(w["nbins"], T, d["time"].data_ptr(), d["exposure"].data_ptr(), d["counts"].data_ptr(), d["sc_pos"].data_ptr(), P,
+                                d["ghat"].data_ptr(), 1, J, d["omega"].data_ptr(), d["a"].data_ptr(), d["b"].data_ptr(), d["amp"].data_ptr(),
+                                d["bkg"].data_ptr(), ll.data_ptr())
+        res["full"] = gather_rows(ll, P_total) if world > 1 else ll
+
+    def e2e():
+        r = ctx.loglik_sky_grid(w["nbins"], pin["time"], pin["exposure"], pin["counts"], pin["sc_pos"], pin["ghat"], pin["omega"], pin["a"],
+                                pin["b"], pin["amp"], pin["bkg"])
+        if world > 1:
+            gather_rows(torch.from_numpy(r).to(dev), P_total)
+
+    def parity():
+        full = res["full"].cpu().numpy()[:, 0]
+        best = int(np.argmax(full))
+        idx = np.unique(np.concatenate([[best], np.random.default_rng(0).choice(P_total, 15, replace=False)]))
+        exp = corc.loglik_sky_grid(w["counts"], w["time"], w["exposure"], w["nbins"], w["sc_pos"], w["ghat"][idx], w["omega"], w["a"], w["b"],
+                                   w["amp"], w["bkg"])[:, 0]
+        err = float(np.abs(full[idx] - exp).max())
+        return {"checker": "oracle/ipn_oracle.c (functions.stan:37-61 + time_delay)", "directions_checked": int(idx.size), "max_abs_nats": err,
+                "tol": 1e-3, "argmax_equal": bool(idx[int(np.argmax(exp))] == best),
+                "largest_deficit_checked_nats": float(exp.max() - exp.min()), "ok": bool(err < 1e-3 and idx[int(np.argmax(exp))] == best)}
+
+    return dict(name=f"config4 sky grid: {P_total} directions (nside {a.nside}) x {D} detectors x {T} bins, 1 draw; {world} rank(s), directions sharded",
+                metric="RFF Poisson loglik grid-points*bins/s", unit="grid-point*bins/s", units_step=float(P_total) * D * T, resident=resident,
+                e2e=e2e, parity=parity, h2d=sum(v.nbytes for v in pin.values()) * world, d2h=P_total * 8, roof=None,
+                dtype="int8 digit planes -> int32 (exact) + compensated f32 / f64 epilogue (chosen per detector)",
+                impl=lambda: {"loglik_impl": ctx.last_loglik_impl})
+
+
+def _wl_config5(a, rank, world, dev, ctx, torch):
+    """Population run: GRBs x 8 detectors, every stage on the GPU: RFF intensity (ipn_rff_eval) -> Poisson counts (ipn_poisson_counts) ->
+    4096-delay grid of every detector against detector 0.  GRBs are independent: sharded over the ranks, only the recovered delays gathered."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import shard_bounds
+    from pyipn_b200.params import fold_draws
+    from pyipn_b200.synth import draw_prior
+
+    lo, hi = shard_bounds(a.grbs, rank, world)
+    T, G, D, J = a.bins, a.delays, 8, 2 * a.k
+    mid = 1e-3 * (np.arange(T) + 0.5)
+    expo = np.full(T, 1e-3)
+    delays = np.linspace(-0.5, 0.5, G)
+    grbs = []
+    for grb in range(lo, hi):
+        rng = np.random.default_rng(1000 + grb)
+        om, b1, b2, sc = draw_prior(rng, a.k, mid[-1] - mid[0])
+        wq, aa, bb = fold_draws(om[0], om[1], b1, b2, 1.0, sc[:, None])
+        true = np.concatenate([[0.0], rng.uniform(-0.4, 0.4, D - 1)])
+        amp = 400.0 * np.exp(rng.normal(0, 0.2, D))
+        grbs.append(dict(w=np.repeat(wq, D, 0), a=np.repeat(aa, D, 0), b=np.repeat(bb, D, 0), true=true, amp=amp))
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    dmid, dexpo, ddel, dbkg = t(mid), t(expo), t(delays), t(np.full(D, 500.0))
+    dg = [dict(w=t(g["w"]), a=t(g["a"]), b=t(g["b"]), true=t(g["true"]), amp=t(g["amp"])) for g in grbs]
+    rates = torch.empty((D, T), dtype=torch.float64, device=dev)
+    counts = torch.empty((D, T), dtype=torch.int64, device=dev)
+    ll = torch.empty((len(grbs), D - 1, G), dtype=torch.float64, device=dev)
+    res = {}
+
+    def resident():
+        for i, g in enumerate(dg):
+            ctx.rff_eval_dev(T, dmid.data_ptr(), D, J, g["w"].data_ptr(), g["a"].data_ptr(), g["b"].data_ptr(), g["true"].data_ptr(),
+                             g["amp"].data_ptr(), rates.data_ptr())
+            ctx.poisson_counts_dev(T, dexpo.data_ptr(), D, rates.data_ptr(), dbkg.data_ptr(), lo + i, counts.data_ptr())
+            for dd in range(1, D):
+                ctx.loglik_delay_grid_dev(T, dmid.data_ptr(), dexpo.data_ptr(), counts[dd].data_ptr(), 1, J, g["w"].data_ptr(), g["a"].data_ptr(),
+                                          g["b"].data_ptr(), g["amp"][dd:].data_ptr(), dbkg.data_ptr(), G, ddel.data_ptr(), ll[i, dd - 1].data_ptr())
+        res["best"] = torch.argmax(ll, dim=2)  # the step's result: recovered delay index per (GRB, detector)
+
+    def e2e():
+        out = np.empty((len(grbs), D - 1), dtype=np.int64)
+        for i, g in enumerate(grbs):
+            r = ctx.rff_eval(mid, g["w"], g["a"], g["b"], g["true"], g["amp"])
+            c = ctx.poisson_counts(expo, r, np.full(D, 500.0), seed=lo + i)
+            for dd in range(1, D):
+                l = ctx.loglik_delay_grid(mid, expo, c[dd], g["w"][:1], g["a"][:1], g["b"][:1], g["amp"][dd:dd + 1], [500.0], delays)
+                out[i, dd - 1] = int(np.argmax(l[:, 0]))
+        res["best_e2e"] = out
+
+    def parity():
+        # the last GRB of this rank's shard is still on the device: its counts and its grids against the oracle on a delay sample
+        i, g = len(grbs) - 1, grbs[-1]
+        c = counts.cpu().numpy()
+        lg = ll[i].cpu().numpy()
+        err, ok_arg = 0.0, True
+        for dd in (1, D - 1):
+            best = int(np.argmax(lg[dd - 1]))
+            idx = np.unique(np.concatenate([np.arange(max(0, best - 2), min(G, best + 3)), [0, G // 3, G - 1]]))
+            exp = corc.loglik_delay_grid(c[dd], mid, expo, g["w"][:1], g["a"][:1], g["b"][:1], g["amp"][dd:dd + 1], [500.0], delays[idx])[:, 0]
+            err = max(err, float(np.abs(lg[dd - 1][idx] - exp).max()))
+            ok_arg &= bool(idx[int(np.argmax(exp))] == best)
+        best_all = res["best"].cpu().numpy()
+        derr = delays[best_all] - np.array([g["true"][1:] for g in grbs])
+        return {"checker": "oracle/ipn_oracle.c on the device-generated counts of the shard's last GRB", "max_abs_nats": err, "tol": 1e-3,
+                "argmax_equal": ok_arg, "delay_error_rms_s": float(np.sqrt(np.mean(derr ** 2))), "grid_step_s": float(delays[1] - delays[0]),
+                "ok": bool(err < 1e-3 and ok_arg)}
+
+    return dict(name=f"config5 population: {a.grbs} GRBs x {D} detectors x {G} delays x {T} bins; {world} rank(s), GRBs sharded",
+                metric="RFF Poisson loglik grid-points*bins/s", unit="grid-point*bins/s", units_step=float(a.grbs) * (D - 1) * G * T,
+                resident=resident, e2e=e2e, parity=parity, h2d=a.grbs * (T * 16 + 3 * D * J * 8 + T * D * 8 * 2), d2h=a.grbs * (D * T * 16 + (D - 1) * G * 8),
+                roof=None, dtype="int8 digit planes -> int32 (exact) + f32 / compensated f32 epilogue; Philox Poisson counts",
+                impl=lambda: {"loglik_impl": ctx.last_loglik_impl, "rff_impl": ctx.last_rff_impl})
+
+
+WORKLOADS = {"rff_eval": _wl_rff_eval, "config2": _wl_config2, "config4": _wl_config4, "config5": _wl_config5}
+
+
+def run_secondary(a, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    from pyipn_b200 import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: pyipn_b200 has no CPU fallback")
+    if a.gpus != world:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE is {world}: launch one rank per GPU (torchrun --nproc-per-node {a.gpus})")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    wl = WORKLOADS[a.workload](a, rank, world, dev, ctx, torch)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        flush.zero_()
+        wl["resident"]()
+        ctx.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms = 0.0
+    ev0.record()
+    for _ in range(a.steps):
+        flush.zero_()
+        wl["resident"]()
+        ctx.synchronize()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = maxr(ev0.elapsed_time(ev1))
+    launches = ctx.launch_count - launches0
+    # device time of the library call(s) alone (no flush): a few extra un-flushed repetitions, events around the call
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wl["resident"]()
+    e1.record()
+    torch.cuda.synchronize()
+    call_ms = e0.elapsed_time(e1)
+    e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    wl["e2e"]()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wl["e2e"]()
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    wl["resident"]()
+    ctx.synchronize()
+    parity = wl["parity"]() if rank == 0 else None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roof = None
+        if wl["roof"]:
+            r = dict(wl["roof"])
+            bytes_rank = wl["units_step"] / world * r.pop("bytes_per_unit")
+            hbm = float(peaks.get("hbm_gbs", 6500.0))
+            ach = bytes_rank / (call_ms * 1e-3) / 1e9
+            roof = dict(r, achieved=ach, peak=hbm, frac=ach / hbm, traffic=None, kernel="operand images + contraction with store epilogue",
+                        peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6500 GB/s",
+                        call_ms=call_ms)
+        line = {"metric": wl["metric"], "value": wl["units_step"] * a.steps / (elapsed_ms * 1e-3), "unit": wl["unit"], "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+                "config": {"workload": wl["name"], "l2": "256 MiB memset between steps, inside the timed region", "seed": 20261019, **wl["impl"]()},
+                "clocks": clocks, "gpu_launches": int(launches), "device_ms_per_call_unflushed": call_ms,
+                "e2e": {"value": wl["units_step"] * e2e_steps / e2e_s, "steps": e2e_steps, "unit": wl["unit"], "h2d_bytes_per_step": int(wl["h2d"]),
+                        "d2h_bytes_per_step": int(wl["d2h"]), "timer": "host perf_counter, max over ranks"},
+                "roofline": roof, "parity": parity}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py --workload {a.workload}: the result is off the oracle: {parity}")
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -187,6 +509,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank, world)
+        return
+    if a.workload != "config3":
+        run_secondary(a, rank, world, local)
         return
     if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # `python bench.py --gpus N` without a launcher: start one rank per GPU ourselves (the driver uses torchrun directly)

@@ -73,6 +73,25 @@ __device__ __forceinline__ float exp2_core(float xf, float t) {
     return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - kMagicBits) << 23));
 }
 
+// The same with the rounding error of the last Horner step recovered: 2^xf 2^xi = hi + lo.  That step (1 + z q, a result in
+// [0.7, 1.5] rounded to 2^-24) is most of the 2.6e-8 rms of exp2_core; 1 - hi is exact there, so one more FMA returns what the
+// rounding dropped.  What remains (~1.2e-8 rms) are the roundings of xf, of z and of q.  Used by the compensated epilogue,
+// whose other terms are exact: on grossly mismatched data the error of u is what is left (it enters the sum with sqrt(sum r_i^2)).
+__device__ __forceinline__ float exp2_core_df(float xf, float t, float& lo) {
+    const float z = fmaf(xf, 0.693145751953125f, xf * 1.4286068203094172e-06f);
+    float p = fmaf(z, 0.00019602585234679282f, 0.0013943274971097708f);
+    p = fmaf(p, z, 0.008333928883075714f);
+    p = fmaf(p, z, 0.041666384786367416f);
+    p = fmaf(p, z, 0.166666641831398f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.0f);
+    const float hi = fmaf(p, z, 1.0f);
+    const float l = fmaf(p, z, 1.0f - hi);
+    const float sc = __int_as_float(((__float_as_int(t) - kMagicBits) << 23) + 0x3f800000);  // 2^xi, |xi| <= 120
+    lo = l * sc;
+    return hi * sc;
+}
+
 __device__ __forceinline__ float exp2_poly(float x) {
     x = fminf(fmaxf(x, -125.0f), 127.0f);
     const float t = x + kMagic;
@@ -91,6 +110,10 @@ __device__ __forceinline__ float exp2_hilo_bounded(float xh, float xl) {
     // a systematic error of 1e-8 .. 1e-7 in u that showed as +2e-2 nats on bright, grossly mismatched data
     const float t = (xh + xl) + kMagic;
     return exp2_core((xh - (t - kMagic)) + xl, t);
+}
+__device__ __forceinline__ float exp2_hilo_df(float xh, float xl, float& lo) {
+    const float t = (xh + xl) + kMagic;
+    return exp2_core_df((xh - (t - kMagic)) + xl, t, lo);
 }
 // the clamped form, for callers without a per-draw bound (the FP32-pipe kernel)
 __device__ __forceinline__ float exp2_hilo_clamped(float xh, float xl) {

@@ -111,14 +111,15 @@ __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&
         const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
         float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
         xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo(xh, xl);
-        // kappa u = q + (eq + klo u), q = fl(khi u)
+        float ul;  // u = 2^x as hi + lo (exp2_core_df)
+        const float u = exp2_hilo_df(xh, xl, ul);
+        // kappa u = q + (eq + klo u + khi ul), q = fl(khi u)
         const float q = c.y * u;
-        float small = fmaf(c.z, u, fmaf(c.y, u, -q));
+        float small = fmaf(c.y, ul, fmaf(c.z, u, fmaf(c.y, u, -q)));
         float d = -q;
         if (HC) {
             const float w = 1.0f + u;
-            const float ew = u - (w - 1.0f);
+            const float ew = (u - (w - 1.0f)) + ul;
             const float y0 = lg2_approx(w);
             const float tm = -y0 + kMagic;
             const float t = exp2_core(-y0 - (tm - kMagic), tm);
