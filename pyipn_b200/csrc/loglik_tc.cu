@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             if (elect_one()) tc_commit(a_tmem_free);  // arrives when this issuer's MMAs of the item have completed
             __syncwarp();
         }
-        if (dbg && lane == 0 && which == 0) {
+        if (dbg && lane == 0 && which == 0 && tile_seq > 0) {  // (an instantiation without draws of its mode leaves the counters alone)
             p.dbg[blockIdx.x * 8 + 2] = w_af;
             p.dbg[blockIdx.x * 8 + 3] = w_bf;
             p.dbg[blockIdx.x * 8 + 4] = w_te;
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
             }
         }
-        if (dbg && warp == 0 && lane == 0) {
+        if (dbg && warp == 0 && lane == 0 && tile_seq > 0) {
             p.dbg[blockIdx.x * 8 + 5] = w_cf;
             p.dbg[blockIdx.x * 8 + 6] = w_tf;
         }
