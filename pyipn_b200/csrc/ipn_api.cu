@@ -642,13 +642,12 @@ int ipn_correlate(ipn_ctx* ctx, int64_t n1, const double* t1, const double* c1, 
     if ((rc = h2d(ctx, ctx->io[1], c1, (size_t)n1 * 8))) return rc;
     if ((rc = h2d(ctx, ctx->io[2], e1, (size_t)n1 * 8))) return rc;
     if ((rc = h2d(ctx, ctx->io[3], t2, (size_t)n2 * 8))) return rc;
-    if ((rc = h2d(ctx, ctx->io[4], c2, (size_t)n2 * 8))) return rc;
-    if ((rc = h2d(ctx, ctx->io[5], e2, (size_t)n2 * 8))) return rc;
+    // light curve 2 stays on the host: its per-bin sums go into the shift-independent plan (correlate.cu)
     if ((rc = ctx->io[6].ensure((size_t)n_max_1 * 8))) return rc;
     if ((rc = ctx->io[7].ensure((size_t)n_max_1 * 8))) return rc;
     begin_timing(ctx);
     rc = launch_correlate(ctx, ctx->io[0].as<double>(), ctx->io[1].as<double>(), ctx->io[2].as<double>(), ctx->io[3].as<double>(),
-                          ctx->io[4].as<double>(), ctx->io[5].as<double>(), n1, i_beg_2, i_end_2, i_beg_1, n_max_1, fscale, dt_1,
+                          c2, e2, n1, i_beg_2, i_end_2, i_beg_1, n_max_1, fscale, dt_1,
                           dt_2, n_sum_2, ctx->io[6].as<double>(), ctx->io[7].as<double>());
     end_timing(ctx);
     if (rc) return rc;

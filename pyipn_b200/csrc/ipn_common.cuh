@@ -109,8 +109,8 @@ int rff_uniform_dev(ipn_ctx* ctx, int64_t T, const double* d_time, double* t0, d
 int launch_bin_events(ipn_ctx* ctx, int64_t n_events, const double* times, double tstart, double dt, int64_t n_edges,
                       int64_t* counts);
 
-int launch_correlate(ipn_ctx* ctx, const double* t1, const double* c1, const double* e1, const double* t2, const double* c2,
-                     const double* e2, int64_t n1, int64_t i_beg_2, int64_t i_end_2, int64_t i_beg_1, int64_t n_max_1,
+int launch_correlate(ipn_ctx* ctx, const double* t1, const double* c1, const double* e1, const double* t2, const double* h_c2,
+                     const double* h_e2, int64_t n1, int64_t i_beg_2, int64_t i_end_2, int64_t i_beg_1, int64_t n_max_1,
                      double fscale, double dt_1, double dt_2, int64_t n_sum_2, double* arr_dt, double* arr_chi);
 
 // bracket a dominant-kernel launch with events (summed by ipn_ctx_synchronize / the host entry points)

@@ -97,18 +97,19 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     TcDraw t;
     t.sigma = (float)ldexp(1.0, e);
     t.ks = (float)ldexp(1.0, -12 - e);
-    // fp32 epilogue error model: every bin's term n y - kappa u is rounded at its own size, so
-    // rms |dll| ~ 1.5e-7 y sqrt(sum n_i^2) with y the typical log2(1 + u) of the bins that hold the counts -- 2-3 for a burst
-    // standing a few times above the background, more when A >> B (measured on the bench data, sum n^2 = 4.5e5: 1.2e-4 rms,
-    // 4.4e-4 max; compensated fp32: 8e-5 / 4.6e-4, dominated by other terms).  The draw goes to the compensated fp32
-    // epilogue when that prediction, times the n_terms detector passes a sky-grid call adds up, exceeds ~1.5e-4 nats, and to
-    // the fp64 epilogue above ~1.5e-3 (bright, coarsely binned data).  flags[1] = IPN_OPT_HIFI: 0 auto, 1 always fp64, 2
-    // always plain fp32, 3 always compensated fp32.
+    // fp32 epilogue error model: every bin's term n y - kappa u is rounded at its own size (and nothing
+    // in fp32 can undo that), so rms |dll| ~ 1.5e-7 y sqrt(sum n_i^2) with y the typical log2(1 + u) of the bins that hold the
+    // counts (measured on the bench data, sum n^2 = 4.5e5: 1.1e-4 rms, but 7e-4 ... 1.0e-3 in the tail of 200 checked grid
+    // points; compensated fp32: 4e-5 rms, 1.4e-4 max).  With the other sources at ~4e-5 and a tail of ~8 sigma over a grid of
+    // 1e7 points, the plain epilogue is only taken where it predicts < 5e-5 nats: n_terms y^2 sum n^2 < 1e5, i.e. faint
+    // data; the compensated fp32 epilogue up to 4e7, the fp64 one beyond (bright, coarsely binned data).  n_terms: the
+    // detector passes a sky-grid call adds up.  flags[1] = IPN_OPT_HIFI: 0 auto, 1 always fp64, 2 always plain fp32, 3
+    // always compensated fp32.
     const double sumsq = *reinterpret_cast<const double*>(flags + 2);
     const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
     // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
     const double crit = ysc * ysc * sumsq * (double)(n_terms > 1 ? n_terms : 1);
-    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0))));
+    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e5 ? 1 : 0))));
     const bool bounded = (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0;
     // the fp32 epilogues evaluate 2^x without clamps (exp2_hilo): a draw whose exponent could leave [-120, 120] -- amplitudes
     // far outside anything the model's priors produce -- is evaluated by the fp64 epilogue whatever the option says

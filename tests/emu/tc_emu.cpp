@@ -220,7 +220,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
     // a draw whose exponent could leave [-120, 120] is evaluated by the fp64 epilogue whatever the option says (the fp32
     // epilogues evaluate 2^x without clamps)
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
-    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 6.0e5 ? 1 : 0));  // n_terms = 1
+    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 1.0e5 ? 1 : 0));  // n_terms = 1
 
     // tc_perm_kernel: bins with counts first (stable)
     std::vector<int> perm;

@@ -77,7 +77,7 @@ def test_config2_full_size_all_epilogues(emu, tmp_path):
     g_true = int(np.argmin(np.abs(w["delays"] - w["true_delay"])))
     idx = np.unique(np.concatenate([np.arange(g_true - 4, g_true + 5), [0, 511, 1777, 3000, 4095]]))
     res, ll, ref = _run_grid(emu, str(tmp_path), w, 0, w["delays"][idx])
-    assert res["Kpad"] == 224 and res["auto_mode"] == 0  # ~1 count per bin: the plain fp32 epilogue is what the device picks
+    assert res["Kpad"] == 224 and res["auto_mode"] == 1  # ~1 count per bin, sum n^2 = 4.5e5: the compensated fp32 epilogue
     err = ll - ref[:, None]
     assert np.abs(err[:, 0]).max() < TOL_NATS, err[:, 0]        # plain fp32
     assert np.abs(err[:, 1]).max() < TOL_NATS, err[:, 1]        # compensated fp32
