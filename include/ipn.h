@@ -44,7 +44,7 @@ extern "C" {
 #define IPN_OPT_PRECISE_W 2   /* FP32-pipe path only: 1 = hi/lo split delay table (default), 0 = single fp32 table */
 #define IPN_OPT_DRAW_BATCH 3  /* max draws per internal batch (bounds the delay-table scratch); 0 = auto     */
 #define IPN_OPT_HIFI 4        /* tcgen05 path epilogue: 0 = auto (per draw: plain fp32; compensated fp32 when the fp32 error model
-                                 predicts more than ~5e-5 nats -- n_terms * sum n_i^2 > 1e5 --; fp64 when > 4e7 or when the draw's
+                                 predicts more than ~5e-5 nats -- n_terms * sum n_i^2 > 2e5 --; fp64 when > 4e7 or when the draw's
                                  exponent is not bounded by 2^120), 1 = fp64, 2 = plain fp32, 3 = compensated fp32             */
 
 #define IPN_OPT_RFF_IMPL 5    /* ipn_rff_eval: 0 = auto (default: the tcgen05 contraction when the bins are uniform -- time[i] =

@@ -56,14 +56,9 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
             v[j] = -fmaf(c.y, u, c.z * u);
         }
     }
-#if !defined(IPN_EPI_KAHAN) || IPN_EPI_KAHAN == 8
-    // pairwise sum of the eight terms (|partial| <= 8 |v|), then ONE Kahan step into the running sum
-    const float g = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    const float yk = g - scomp;
-    const float tt = ssum + yk;
-    scomp = (tt - ssum) - yk;
-    ssum = tt;
-#elif IPN_EPI_KAHAN == 2
+    // the terms are rounded at their own size, and so is every partial sum: a pairwise sum of all eight before one Kahan step
+    // (|partial| <= 8 |v|) turned out to be most of this epilogue's error on data with bright bins (emulated on the bench
+    // draws: 1.1e-4 nats rms against 6.8e-5 with a Kahan step per PAIR, 5.9e-5 with one per term) -- so: pairs
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
         const float yk = (v[j] + v[j + 1]) - scomp;
@@ -71,15 +66,6 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
         scomp = (tt - ssum) - yk;
         ssum = tt;
     }
-#else
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float yk = v[j] - scomp;
-        const float tt = ssum + yk;
-        scomp = (tt - ssum) - yk;
-        ssum = tt;
-    }
-#endif
 }
 
 // Store epilogue (ipn_rff_eval on uniform bins through the same contraction): no Poisson terms, just u = 2^x of the eight bins.

@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             double hacc = 0.0;
             const double ksd = (double)ks;
             const double sgn = MODE == EPI_STORE ? p.sgn[sl] : 0.0;
+            const bool zero_plain = MODE == EPI_COMP && (p.td[sl].pad & 1);  // tiles without counts take the plain fp32 unit
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
                 const uint32_t tb = tile_seq % NBUF, tph = (tile_seq / NBUF) & 1;
                 const uint32_t cs = tile_seq % NCST, cph = (tile_seq / NCST) & 1;
@@ -623,6 +624,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
                             else if (MODE == EPI_COMP && has_counts)
                                 epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                            else if (MODE == EPI_COMP && zero_plain)  // bins without counts: - kappa u is small unless the model is grossly off
+                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
                                 epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (has_counts)

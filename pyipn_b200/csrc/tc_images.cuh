@@ -101,7 +101,7 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     // in fp32 can undo that), so rms |dll| ~ 1.5e-7 y sqrt(sum n_i^2) with y the typical log2(1 + u) of the bins that hold the
     // counts (measured on the bench data, sum n^2 = 4.5e5: 1.1e-4 rms, but 7e-4 ... 1.0e-3 in the tail of 200 checked grid
     // points; compensated fp32: 4e-5 rms, 1.4e-4 max).  With the other sources at ~4e-5 and a tail of ~8 sigma over a grid of
-    // 1e7 points, the plain epilogue is only taken where it predicts < 5e-5 nats: n_terms y^2 sum n^2 < 1e5, i.e. faint
+    // 1e7 points, the plain epilogue (1.0e-7 sqrt(.) with its Kahan step per pair) is only taken where it predicts < 5e-5 nats: n_terms y^2 sum n^2 < 2e5, i.e. faint
     // data; the compensated fp32 epilogue up to 4e7, the fp64 one beyond (bright, coarsely binned data).  n_terms: the
     // detector passes a sky-grid call adds up.  flags[1] = IPN_OPT_HIFI: 0 auto, 1 always fp64, 2 always plain fp32, 3
     // always compensated fp32.
@@ -109,12 +109,15 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
     const double ysc = isfinite(c) ? fmax(1.0, (double)dc[s].c_hi) : 1.0;
     // t.hifi = epilogue mode of the draw: 0 fp32, 1 compensated fp32, 2 fp64 (EPI_* below)
     const double crit = ysc * ysc * sumsq * (double)(n_terms > 1 ? n_terms : 1);
-    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 1.0e5 ? 1 : 0))));
+    t.hifi = flags[1] == 1 ? 2 : (flags[1] == 2 ? 0 : (flags[1] == 3 ? 1 : (crit > 4.0e7 ? 2 : (crit > 2.0e5 ? 1 : 0))));
     const bool bounded = (isfinite(c) ? c : 0.0) + sumw * (1.0 + 1e-6) + 1e-3 <= 120.0;
     // the fp32 epilogues evaluate 2^x without clamps (exp2_hilo): a draw whose exponent could leave [-120, 120] -- amplitudes
     // far outside anything the model's priors produce -- is evaluated by the fp64 epilogue whatever the option says
     if (!bounded) t.hifi = 2;
-    t.pad = 0;
+    // bit 0: in the compensated epilogue, tiles WITHOUT counts take the plain fp32 unit (28 instead of 37 instructions per
+    // bin): their terms are - kappa u, far below the size at which fp32 rounding matters unless the model puts many counts
+    // where the data have none -- which is what most pixels of a sky grid do for the far detectors, so not there
+    t.pad = n_terms <= 1 ? 1 : 0;
     td[sl] = t;
 }
 

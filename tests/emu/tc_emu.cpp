@@ -220,7 +220,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
     // a draw whose exponent could leave [-120, 120] is evaluated by the fp64 epilogue whatever the option says (the fp32
     // epilogues evaluate 2^x without clamps)
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
-    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 1.0e5 ? 1 : 0));  // n_terms = 1
+    const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 2.0e5 ? 1 : 0));  // n_terms = 1
 
     // tc_perm_kernel: bins with counts first (stable)
     std::vector<int> perm;
@@ -410,7 +410,8 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                             epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
                         } else {
                             epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
-                            epi_units8_comp<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
+                            // n_terms = 1 (TcDraw::pad bit 0): tiles without counts take the plain unit in the compensated epilogue too
+                            epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
                         }
                         epi_units8_hifi(t2, t3, t4, t5, cp, ksd, hacc[slot]);
                     }

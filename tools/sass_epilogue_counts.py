@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "pyipn_b200", "csrc", "build", "loglik_tc.o")
-MODES = {0: "fp32 (per-bin logarithm)", 1: "compensated fp32", 2: "fp64", 3: "product (opt-in)"}
+MODES = {0: "fp32 (per-bin logarithm)", 1: "compensated fp32", 2: "fp64", 3: "store (ipn_rff_eval)"}
 
 
 def blocks(mode):
