@@ -35,14 +35,26 @@ rff_eval_kernel(int64_t T, const double* __restrict__ time, int64_t S0, int64_t 
     double* s_b = s_w + 2 * J;
     __shared__ unsigned int s_wmax;                       // bits of max_j |wh|
     __shared__ float s_amp2;                              // sum_j a_j^2 + b_j^2 of the draw
-    const int64_t n_items = S * tiles_per_draw;
     int64_t cur_s = -1;
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int64_t sl = item / tiles_per_draw;
+    // Unmasked: items (draw, tile) strided over the CTAs.  Masked run behind the contraction route (loglik_tc.cu:
+    // run_rff_eval_tc; only the draws it left out, TcDraw::hifi == 2): draw-major per CTA -- CTA c takes draws c, c + grid, ...
+    // and one look at a draw's mode skips all its tiles.
+    const int64_t n_it = only ? ((S + gridDim.x - 1) / gridDim.x) * tiles_per_draw : S * tiles_per_draw;
+    for (int64_t it = only ? 0 : (int64_t)blockIdx.x; it < n_it; it += only ? 1 : (int64_t)gridDim.x) {
+        int64_t sl, tile;
+        if (only) {
+            sl = (int64_t)blockIdx.x + (it / tiles_per_draw) * (int64_t)gridDim.x;
+            tile = it % tiles_per_draw;
+            if (sl >= S) break;
+            if (only[sl].hifi != 2) {
+                it += tiles_per_draw - 1 - tile;  // on to this CTA's next draw
+                continue;
+            }
+        } else {
+            sl = it / tiles_per_draw;
+            tile = it - sl * tiles_per_draw;
+        }
         const int64_t s = S0 + sl;  // draws S0 .. S0 + S - 1
-        const int64_t tile = item - sl * tiles_per_draw;
-        // masked run behind the contraction route (loglik_tc.cu: run_rff_eval_tc): only the draws it left out
-        if (only && only[sl].hifi != 2) continue;
         if (s != cur_s) {
             __syncthreads();
             if (threadIdx.x == 0) s_wmax = 0u;
