@@ -73,7 +73,7 @@ def ncu(tag, rep_name="prof_bench.ncu-rep", label="loglik_tc_kernel", what=None,
     rec = {h: (u, v) for h, u, v in zip(head, units, vals)}
     with open(os.path.join(PROF, f"{tag}_ncu_{label}.txt"), "w") as f:
         f.write(what or ("# ncu --set full --clock-control none --import-source on capture of the hot kernel inside `python bench.py --draws 500 --steps 2 "
-                         "--warmup 1 --no-cpu-baseline`\n# (third launch of the fp32-epilogue instantiation; one launch = one draw batch of the bench step)\n\n"))
+                         "--warmup 1 --no-cpu-baseline`\n# (third launch of the compensated-epilogue instantiation, the one the bench data get; one launch = one draw batch of the bench step)\n\n"))
         for k in ("Kernel Name", "Grid Size", "Block Size"):
             f.write(f"{k} [] = {rec[k][1]}\n")
         for k in KEEP:
