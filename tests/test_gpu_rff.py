@@ -182,3 +182,21 @@ def test_rff_eval_route_follows_the_bins(ctx):
     ctx.synchronize()
     assert ctx.last_rff_impl == 2
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("J", [1, 3, 101, 107])
+@pytest.mark.parametrize("uniform", [False, True])
+def test_rff_eval_odd_number_of_frequencies(ctx, J, uniform):
+    """J odd: the direct kernel's float4 parameter table must stay 16-byte aligned behind an odd number of doubles (it was
+    not: misaligned LDS.128, a sticky fault), and the contraction pads 2J + 8 rows up to a multiple of 32 whatever J is."""
+    rng = np.random.default_rng(J)
+    T, S = 3000, 3
+    time = 0.5e-3 + 1e-3 * np.arange(T) if uniform else np.sort(rng.uniform(0.0, 3.0, T))
+    omega = rng.normal(size=(S, J)) * 3.0
+    a = rng.normal(size=(S, J)) * 0.2
+    b = rng.normal(size=(S, J)) * 0.2
+    shift, amp = rng.normal(size=S), np.exp(rng.normal(size=S))
+    got = ctx.rff_eval(time, omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == (2 if uniform else 1)
+    for s in range(S):
+        np.testing.assert_allclose(got[s], amp[s] * np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])), rtol=RTOL)
