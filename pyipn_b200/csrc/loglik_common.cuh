@@ -37,6 +37,44 @@ struct TcDraw {
     int pad;
 };
 
+// ---- order of the bins in the Phi image of the tcgen05 path ----
+// Bins with counts cost the epilogue 2.4x the instructions of bins without (the logarithm), and with twelve digit-plane products
+// a tile of either kind costs the tensor pipe the same: tiles WITH counts are epilogue-bound (the tensor pipe idles), tiles
+// WITHOUT are tensor-bound (the epilogue warps idle).  So the two kinds are interleaved: the bins are still partitioned (counts
+// first, original order within each class, so every 32-bin tile is homogeneous and a tile without counts skips the logarithm),
+// but the TILES are laid out  C Z Z C | C Z Z C | ...  (C: with counts, Z: without) while both kinds last -- any two
+// consecutive tiles hold one of each, and each of the four epilogue warps of a lane quarter, which take units of every other
+// tile, alternates between the kinds as well.  Only full tiles take part; what is left of the longer class follows in its
+// natural order (-DIPN_TC_INTERLEAVE=0: everything in natural order, the round-1 layout).
+// tc_bin_position: position in the permuted order of the bin with rank r within its class (n_nz bins with counts among T).
+#ifndef IPN_TC_INTERLEAVE
+#define IPN_TC_INTERLEAVE 1
+#endif
+__device__ __forceinline__ long long tc_bin_position(bool has_counts, long long r, long long n_nz, long long T, int TN) {
+    const long long Tc = (n_nz + TN - 1) / TN;   // tiles that start with a bin with counts
+    const long long hole = Tc * TN - n_nz;       // rows of the last of them that bins without counts fill up
+    const long long n_z = T - n_nz;
+    const long long Fz = n_z > hole ? (n_z - hole) / TN : 0;  // full tiles without counts
+    const long long Fc = n_z >= hole ? Tc : Tc - 1;           // full tiles with counts
+    long long m = Fc < Fz ? Fc : Fz;                          // tiles of each kind that are interleaved
+    if (!IPN_TC_INTERLEAVE || m < 0) m = 0;
+    long long tile, row;
+    if (has_counts) {
+        const long long j = r / TN;
+        row = r - j * TN;
+        tile = j < m ? 4 * (j / 2) + ((j & 1) ? 3 : 0) : m + j;
+    } else if (r < hole) {
+        const long long j = Tc - 1;
+        row = (n_nz - j * TN) + r;
+        tile = j < m ? 4 * (j / 2) + ((j & 1) ? 3 : 0) : m + j;
+    } else {
+        const long long rr = r - hole, j = rr / TN;
+        row = rr - j * TN;
+        tile = j < m ? 4 * (j / 2) + 1 + (j & 1) : Tc + j;
+    }
+    return tile * TN + row;
+}
+
 #ifndef IPN_HOST_EMU
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

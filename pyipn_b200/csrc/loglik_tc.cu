@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     uint64_t* w5_full = a_tmem_free + 1;     // fifth W digit plane of the item is in shared memory (-> both issuers)
     uint64_t* t6_empty = w5_full + 1;        // [2] level-6 accumulator drained by the epilogue of tile n - 1 (-> issuer of tile n, n % 2)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t6_empty + 2);
-    volatile uint32_t* prog = tmem_slot + 4;  // [24] last wait of every warp (time-out diagnostics)
-    static_assert(NTHREADS / 32 <= 24, "prog[] holds one word per warp");
+    volatile uint32_t* prog = tmem_slot + 4;  // [32] last wait of every warp (time-out diagnostics; the record keeps the first 24)
+    static_assert(NTHREADS / 32 <= 32, "prog[] holds one word per warp");
 
     // warp index made provably warp-uniform so the role branches (and everything inside them) stay on the
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
@@ -703,7 +703,7 @@ static int run_tc_grid(ipn_ctx* ctx, int64_t T, const double* time, const double
     const uint32_t a_bytes = PW * a_plane, b_dig = PP * b_plane, b_bytes = b_dig + CONST_BYTES;  // b_bytes = global tile image
     if ((rc0 = ensure_phitab(ctx))) return rc0;
     // fifth W plane (resident) + two-plane staging buffer + Phi ring + constants ring + barriers + TMEM slot + wait log
-    const size_t smem = 3 * (size_t)a_plane + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (7 + NBUF + NTF + NBFULL + NBST + 2 * NCST) * 8 + 16 + 24 * 4;
+    const size_t smem = 3 * (size_t)a_plane + NBST * (size_t)b_dig + (size_t)NCST * CONST_BYTES + (7 + NBUF + NTF + NBFULL + NBST + 2 * NCST) * 8 + 16 + 32 * 4;
 
     // draws per batch: bound the operand-image scratch (T/64 Phi tiles x ~44 KB per draw) to ~6 GiB
     const size_t p_per_draw = (size_t)n_bt * b_bytes, w_per_draw = (size_t)n_dt * a_bytes;

@@ -271,7 +271,9 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
         *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
         if (row == 0) {
             float4 f;
-            f.x = ((int64_t)bt * tc::TN < (int64_t)*n_nz) ? 1.0f : 0.0f;  // tile holds at least one bin with counts
+            // the tile holds at least one bin with counts: its first bin does (tiles are homogeneous up to the one boundary tile,
+            // which starts with the last bins with counts; the thread of row 0 is here and has the tile's first bin in i)
+            f.x = (valid && counts[i] > 0) ? 1.0f : 0.0f;
             f.y = f.z = f.w = 0.0f;
             *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
         }

@@ -6,6 +6,7 @@
 #ifndef IPN_HOST_EMU
 #include "ipn_common.cuh"
 #endif
+#include "loglik_common.cuh"  // tc_bin_position
 
 namespace ipn {
 
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(1024) tc_perm_kernel(int64_t T, const int64_t*
     int woff = 0;
     for (int w = 0; w < warp; ++w) woff += wsum[w];
     const int nz_before = s_before + woff + incl - flag;
-    if (i < T) perm[flag ? nz_before : (int64_t)s_total + (i - nz_before)] = (int)i;
+    // rank within the class -> position: tiles of the two classes interleaved (tc_bin_position, loglik_common.cuh)
+    if (i < T) perm[tc_bin_position(flag != 0, flag ? nz_before : i - nz_before, s_total, T, 32)] = (int)i;
 }
 
 }  // namespace ipn

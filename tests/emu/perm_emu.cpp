@@ -61,10 +61,35 @@ int main(int argc, char** argv) {
         return 0;
     };
 
-    // the partition of the default epilogues: bins with counts first, stable
-    std::vector<int> want(T);
-    for (int64_t i = 0; i < T; ++i) want[i] = (int)i;
-    std::stable_sort(want.begin(), want.end(), [&](int a, int b) { return (counts[a] > 0) > (counts[b] > 0); });
+    // expected order, built tile by tile (independently of tc_bin_position's closed form): bins with counts and bins without,
+    // each class in its original order; the last tile of the first class is filled up with the first bins of the second; of
+    // the FULL tiles of both classes the first m = min(#full C, #full Z) are laid out C Z Z C | C Z Z C | ..., the rest follows
+    // in natural order (all remaining C tiles, then the remaining Z tiles, a partial one last)
+    std::vector<int> cls_c, cls_z;
+    for (int64_t i = 0; i < T; ++i) (counts[i] > 0 ? cls_c : cls_z).push_back((int)i);
+    std::vector<std::vector<int>> tc_tiles, tz_tiles;
+    size_t zi = 0;
+    for (size_t k = 0; k < cls_c.size(); k += 32) tc_tiles.emplace_back(cls_c.begin() + k, cls_c.begin() + std::min(cls_c.size(), k + 32));
+    if (!tc_tiles.empty())
+        while (tc_tiles.back().size() < 32 && zi < cls_z.size()) tc_tiles.back().push_back(cls_z[zi++]);
+    for (; zi < cls_z.size(); zi += 32) tz_tiles.emplace_back(cls_z.begin() + zi, cls_z.begin() + std::min(cls_z.size(), zi + 32));
+    size_t full_c = 0, full_z = 0;
+    for (auto& t : tc_tiles) full_c += t.size() == 32;
+    for (auto& t : tz_tiles) full_z += t.size() == 32;
+    const size_t m = IPN_TC_INTERLEAVE ? std::min(full_c, full_z) : 0;
+    std::vector<std::vector<int>> order(2 * m);
+    for (size_t j = 0; j < m; ++j) {
+        order[4 * (j / 2) + ((j & 1) ? 3 : 0)] = tc_tiles[j];
+        order[4 * (j / 2) + 1 + (j & 1)] = tz_tiles[j];
+    }
+    for (size_t j = m; j < tc_tiles.size(); ++j) order.push_back(tc_tiles[j]);
+    for (size_t j = m; j < tz_tiles.size(); ++j) order.push_back(tz_tiles[j]);
+    std::vector<int> want;
+    for (auto& t : order) want.insert(want.end(), t.begin(), t.end());
+    if ((int64_t)want.size() != T) {
+        std::printf("expected order has %zu entries for T = %lld\n", want.size(), (long long)T);
+        return 1;
+    }
     if (n_blk > 0) shim::launch(ipn::tc_perm_count_kernel, n_blk, 1024, T, counts.data(), blk_cnt.data(), blk_sq.data());
     shim::launch(ipn::tc_perm_kernel, n_blk > 0 ? n_blk : 1, 1024, T, counts.data(), n_blk, blk_cnt.data(), blk_sq.data(), perm.data(),
                  flags, 0);

@@ -222,14 +222,17 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
     const double xmax = (std::isfinite(cabs) ? cabs : 0.0) + sumw * (1.0 + 1e-6) + 1e-3;
     const int auto_mode = xmax > 120.0 ? 2 : (crit > 4.0e7 ? 2 : (crit > 2.0e5 ? 1 : 0));  // n_terms = 1
 
-    // tc_perm_kernel: bins with counts first (stable)
-    std::vector<int> perm;
-    perm.reserve(T);
-    for (int64_t i = 0; i < T; ++i)
-        if (counts[i] > 0) perm.push_back((int)i);
-    const int64_t n_nz = (int64_t)perm.size();
-    for (int64_t i = 0; i < T; ++i)
-        if (!(counts[i] > 0)) perm.push_back((int)i);
+    // tc_perm_kernel: bins with counts and bins without, each class in its original order, tiles of the two classes interleaved
+    int64_t n_nz = 0;
+    for (int64_t i = 0; i < T; ++i) n_nz += counts[i] > 0;
+    std::vector<int> perm((size_t)T, -1);
+    {
+        int64_t rc = 0, rz = 0;
+        for (int64_t i = 0; i < T; ++i) {
+            const bool f = counts[i] > 0;
+            perm[(size_t)tc_bin_position(f, f ? rc++ : rz++, n_nz, T, cfg::TN)] = (int)i;
+        }
+    }
 
     // tc_phitab_kernel: the 1024-point unit circle in 2^-30 fixed point
     std::vector<PhiTabEntry> phitab(kPhiTabSize);
@@ -342,7 +345,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                     img[pl * b_plane + ((size_t)(k / 16) * cfg::TN + row) * 16 + k % 16] = (uint8_t)P[((size_t)pl * Tpad + pos) * Kpad + k];
             std::memcpy(img + 4 * b_plane + (size_t)row * 16, &cst[pos], 16);
             if (row == 0) {
-                const float4 fl = {(pos < n_nz) ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
+                const float4 fl = {counts[perm[pos]] > 0 ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
                 std::memcpy(img + 4 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
             }
         }
@@ -371,7 +374,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
             double hacc[cfg::EPI_SLOTS] = {};
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const bool has_counts = (int64_t)bt * cfg::TN < n_nz;
+                const bool has_counts = counts[perm[(size_t)bt * cfg::TN]] > 0;  // the tile's first bin (tc_pimg_kernel's flag)
                 // the eleven digit-plane products of the tile (int32, exact), loglik_tc.cu header
                 for (int r = 0; r < cfg::TN; ++r) {
                     const size_t pos = (size_t)bt * cfg::TN + r;
