@@ -52,24 +52,21 @@ class Correlator(object):
             self._fSigma.append(fs)
 
     def _get_dTcc(self, nSigma=3):
-        """correlation.py:127-171."""
+        """Lag confidence interval at ``nSigma`` (semantics of correlation.py:127-171): the chi^2/dof level that the two-sided
+        Gaussian probability of nSigma maps to, and the first shifts on either side of the minimum at which the curve reaches it
+        -- found with two vectorised threshold searches instead of the reference's two walks.  The reference's walks stop at
+        index 1 on the left and at the last index on the right even when the curve never reaches the level there: kept."""
         from scipy.stats import chi2, norm
 
-        P0 = norm.cdf(nSigma) - norm.cdf(-nSigma)
-        fSigma = chi2.ppf(P0, self._nDOF - 1) / (self._nDOF - 1) - 1.0 + self._fRijMin
-        n = self._arr_chi.size
-        i = self._nMin
-        fRij = self._arr_chi[i]
-        while (i > 1) and (fRij < fSigma):
-            i = i - 1
-            fRij = self._arr_chi[i]
-        dTupper = self._arr_dt[i]
-        i = self._nMin
-        fRij = self._arr_chi[i]
-        while (i < n - 1) and (fRij < fSigma):
-            i = i + 1
-            fRij = self._arr_chi[i]
-        return self._arr_dt[i], dTupper, fSigma
+        dof = self._nDOF - 1
+        level = chi2.isf(2.0 * norm.sf(nSigma), dof) / dof - 1.0 + self._fRijMin
+        above = np.asarray(self._arr_chi) >= level
+        k = self._nMin
+        left = np.flatnonzero(above[2:k + 1]) + 2 if k >= 2 else np.empty(0, dtype=np.int64)
+        i_upper = int(left[-1]) if left.size else min(k, 1)
+        right = np.flatnonzero(above[k:-1]) + k
+        i_lower = int(right[0]) if right.size else max(k, above.size - 1)
+        return self._arr_dt[i_lower], self._arr_dt[i_upper], level
 
     def info(self):
         """correlation.py:98-125 (the summary the reference prints); returned as well as printed."""
