@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 session 4: where does the 12-product tile spend its time?  (hooks builds: role isolation; level-6 variants)
-mkdir -p gpurun_out/r2s4; O=gpurun_out/r2s4
+mkdir -p gpurun_out/roles; O=gpurun_out/roles
 cat > /tmp/period.py <<'PY'
 import sys, os
 sys.path.insert(0, ".")
@@ -14,7 +14,7 @@ for _ in range(2):
     ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
 print("ok", ctx.last_kernel_ms, ctx.last_main_kernel)
 PY
-for v in default l6ts l6ss; do
+for v in default; do
   lib=pyipn_b200/libipn_b200_${v}_hooks.so; [ $v = default ] && lib=pyipn_b200/libipn_b200_hooks.so
   for hook in none IPN_TC_SKIP_MATH=1 IPN_TC_SKIP_MMA=1; do
     echo "== $v $hook"

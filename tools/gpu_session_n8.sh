@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 multi-GPU session (gpurun --gpus 8): strong and weak scaling of the headline bench, pixel-sharded config 4, GRB-sharded config 5
-mkdir -p gpurun_out/r2n8; O=gpurun_out/r2n8
+mkdir -p gpurun_out/session_n8; O=gpurun_out/session_n8
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531"
 timeout 600 $TR bench.py --gpus 8 --steps 10 --warmup 3 > $O/bench_n8_strong.json 2> $O/bench_n8_strong.err; echo "strong rc=$?"; cat $O/bench_n8_strong.json | cut -c1-600
 timeout 600 $TR bench.py --gpus 8 --steps 4 --warmup 3 --draws-per-gpu 500 --no-cpu-baseline > $O/bench_n8_weak.json 2> $O/bench_n8_weak.err; echo "weak rc=$?"; cat $O/bench_n8_weak.json | cut -c1-300

@@ -1,5 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out/r2s8; O=gpurun_out/r2s8
+mkdir -p gpurun_out/workloads; O=gpurun_out/workloads
 for wl in rff_eval config2 config4; do
   timeout 600 python bench.py --workload $wl --steps 3 --warmup 2 > $O/bench_$wl.json 2> $O/bench_$wl.err; echo "bench $wl rc=$?"; tail -2 $O/bench_$wl.err; cat $O/bench_$wl.json
 done
