@@ -410,3 +410,21 @@ def test_many_draws_full_length_vs_oracle(ctx):
         e = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"][[s]], w["a"][[s]], w["b"][[s]],
                                    w["amp"][[s]], w["bkg"][[s]], w["delays"][win])[:, 0]
         assert win[int(np.argmax(e))] == b
+
+
+@pytest.mark.parametrize("T,G,S", [(1_000_003, 130, 2), (3001, 70_001, 1)])
+def test_large_shapes_vs_oracle(ctx, T, G, S):
+    """A million bins (31 251 tiles, ragged last one, 245 items per delay tile) and seventy thousand delays (547 delay tiles, the
+    last one with a single row): a subsample of (delay, draw) pairs against the C oracle, arg-max on a window."""
+    from oracle import c_oracle as corc
+    from pyipn_b200.synth import delay_grid_workload
+
+    corc.build()
+    w = delay_grid_workload(T=T, G=G, S=S, dt_bin=1e-4 if T > 100_000 else 1e-2, bkg=5000.0 if T > 100_000 else 50.0)
+    ll = ctx.loglik_delay_grid(w["time"], w["exposure"], w["counts"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    assert ll.shape == (G, S) and np.all(np.isfinite(ll))
+    best = int(np.argmax(ll[:, 0]))
+    idx = np.unique(np.clip([0, best - 1, best, best + 1, G // 3, G - 2, G - 1], 0, G - 1))
+    exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"][idx])
+    assert np.abs(ll[idx] - exp).max() < ATOL
+    assert idx[int(np.argmax(exp[:, 0]))] == best

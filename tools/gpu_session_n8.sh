@@ -8,4 +8,4 @@ timeout 600 $TR bench.py --gpus 8 --workload config4 --steps 5 --warmup 3 > $O/b
 timeout 900 $TR bench.py --gpus 8 --workload config5 --grbs 1000 --steps 1 --warmup 1 > $O/bench_n8_config5.json 2> $O/bench_n8_config5.err; echo "config5 rc=$?"; cat $O/bench_n8_config5.json | cut -c1-300
 timeout 600 $TR bench.py --gpus 8 --workload rff_eval --draws 8000 --steps 4 --warmup 3 > $O/bench_n8_rff.json 2> $O/bench_n8_rff.err; echo "rff rc=$?"; cat $O/bench_n8_rff.json | cut -c1-300
 timeout 600 python bench.py --gpus 1 --steps 4 --warmup 3 --no-cpu-baseline > $O/bench_n1_same_box.json 2> $O/bench_n1.err; echo "n1 rc=$?"; cat $O/bench_n1_same_box.json | cut -c1-300
-tail -3 $O/*.err
+for f in $O/*.err; do tail -2 $f; done
