@@ -292,6 +292,21 @@ __device__ __forceinline__ bool sincos_phase_q30(float wh, float wl, float th, f
     return true;
 }
 
+// the same for callers that have bounded |wh th| < 2^22 for all their frequencies at once (tc_pimg_kernel: per bin)
+__device__ __forceinline__ void sincos_phase_q30_bounded(float wh, float wl, float th, float tl, const PhiTabEntry* __restrict__ tab,
+                                                         int& qs, int& qc) {
+    const float ph = wh * th;
+    const float e = fmaf(wh, th, -ph);
+    const float cross = fmaf(wh, tl, fmaf(wl, th, e));
+    const float k = (ph + kMagic) - kMagic;
+    sincos_turns_q30(ph - k, cross, tab, qs, qc);
+}
+
+// The four signed 8-bit digits of q (|q| <= 2^30 + 2^22) packed into one word, lowest digit in byte 0: adding 128 to each of
+// the three low bytes turns the signed digits into unsigned ones with the carries resolved by the addition itself, and the
+// XOR takes the bias off again (split_digits4, loglik_epilogue.cuh, gives the same digits one at a time).
+__device__ __forceinline__ unsigned pack_digits4(int q) { return ((unsigned)q + 0x00808080u) ^ 0x00808080u; }
+
 // fp64 phase -> (sin, cos) in fp32 with ~2e-8 rms error regardless of |phase| (< 2^40 or so).
 __device__ __forceinline__ void sincos_phase(double ph, float& s, float& c) {
     const double kq = rint(ph * 0.15915494309189534561);

@@ -774,7 +774,7 @@ static int run_tc_grid(ipn_ctx* ctx, int64_t T, const double* time, const double
         tc_wimg_kernel<<<dim3(Kpad / 16, n_dt, Sb), 128, 0, ctx->stream>>>(S0, (int)J, Kpad, omega, a, b, d_dc, d_td, G, delays,
                                                                             delay_stride, n_dt, a_bytes, a_plane, d_W);
         if (n_bt > 0)
-            tc_pimg_kernel<<<dim3(n_bt, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
+            tc_pimg_kernel<<<dim3((n_bt + PIMG_TILES - 1) / PIMG_TILES, Sb), 256, 0, ctx->stream>>>(S0, (int)J, Kpad, T, time, exposure, counts, d_perm, d_nnz,
                                                                      omega, d_dc, d_td, ctx->phitab.as<PhiTabEntry>(), n_bt, b_bytes, b_plane, d_P);
         ctx->launches += 3;
         IPN_CUDA_CHECK(cudaGetLastError());

@@ -182,10 +182,53 @@ __global__ void tc_phitab_kernel(PhiTabEntry* __restrict__ tab) {
     tab[k] = e;
 }
 
-// Phi digit planes + Poisson constants of one (draw, tile of TN permuted bins).
+// Phi digit planes + Poisson constants of PIMG_TILES consecutive tiles (TN permuted bins each) of one draw.
 // 256 threads: row = tid % 32, eight threads per row interleave the 16-wide K chunks.
 // Phi = (p1 2^24 + p2 2^16 + p3 2^8 + p4) 2^-30 with the sine / cosine formed directly in 2^-30 fixed point (PP = 4), or the
 // round-1 variant (p1 2^16 + p2 2^8 + p3) 2^-22 from fp32 polynomials (PP = 3); p1 is the same digit in both.
+constexpr int PIMG_TILES = 4;  // tiles per CTA: the 8 KB table and the draw's frequencies are staged once for all of them
+
+// one 16-wide K chunk (8 sine / cosine pairs) of one bin -> 16 packed digit words -> the four planes' 16-byte rows
+template <bool BOUNDED>
+__device__ __forceinline__ void pimg_chunk_q30(int kc, int J, bool valid, float th, float tl, double t, const float2* __restrict__ s_w,
+                                               const PhiTabEntry* __restrict__ s_tab, const double* __restrict__ omega_s,
+                                               uint8_t* __restrict__ img, uint32_t b_plane, int row) {
+    unsigned w[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 2) {
+        const int k = kc * 16 + kk;
+        int q0 = 0, q1 = 0;
+        if (valid) {
+            if (k < 2 * J) {
+                const float2 wv = s_w[k >> 1];
+                if (BOUNDED) {
+                    sincos_phase_q30_bounded(wv.x, wv.y, th, tl, s_tab, q1, q0);
+                } else if (!sincos_phase_q30(wv.x, wv.y, th, tl, s_tab, q1, q0)) {
+                    double sn, cn;
+                    sincos(omega_s[k >> 1] * t, &sn, &cn);
+                    q0 = (int)llrint(cn * 1073741824.0);
+                    q1 = (int)llrint(sn * 1073741824.0);
+                }
+            } else {
+                q0 = q1 = 1073741824;  // constant rows: Phi = 1
+            }
+        }
+        w[kk] = pack_digits4(q0);      // cos row
+        w[kk + 1] = pack_digits4(q1);  // sin row
+    }
+    // byte transpose: plane pl (0 = most significant digit) takes byte 3 - pl of each of the 16 words
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) {
+        const int sh = 24 - 8 * pl;
+        int4 o;
+        o.x = (int)(((w[0] >> sh) & 0xffu) | (((w[1] >> sh) & 0xffu) << 8) | (((w[2] >> sh) & 0xffu) << 16) | (((w[3] >> sh) & 0xffu) << 24));
+        o.y = (int)(((w[4] >> sh) & 0xffu) | (((w[5] >> sh) & 0xffu) << 8) | (((w[6] >> sh) & 0xffu) << 16) | (((w[7] >> sh) & 0xffu) << 24));
+        o.z = (int)(((w[8] >> sh) & 0xffu) | (((w[9] >> sh) & 0xffu) << 8) | (((w[10] >> sh) & 0xffu) << 16) | (((w[11] >> sh) & 0xffu) << 24));
+        o.w = (int)(((w[12] >> sh) & 0xffu) | (((w[13] >> sh) & 0xffu) << 8) | (((w[14] >> sh) & 0xffu) << 16) | (((w[15] >> sh) & 0xffu) << 24));
+        *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpad, int64_t T, const double* __restrict__ time,
                                                       const double* __restrict__ exposure, const int64_t* __restrict__ counts,
                                                       const int* __restrict__ perm, const int* __restrict__ n_nz,
@@ -194,88 +237,88 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
                                                       uint32_t b_bytes, uint32_t b_plane, uint8_t* __restrict__ Pimg) {
     const int row = threadIdx.x & (tc::TN - 1);
     const int kg = threadIdx.x / tc::TN;
-    const int bt = blockIdx.x;
     const int sl = blockIdx.y;
     const int64_t s = S0 + sl;
-    const int64_t pos = (int64_t)bt * tc::TN + row;
-    const bool valid = pos < T;
-    const int64_t i = valid ? perm[pos] : 0;
-    const double t = valid ? time[i] : 0.0;
-    const float th = (float)t, tl = (float)(t - (double)(float)t);
-    uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
     // omega / 2 pi of this draw as fp32 hi + lo: the phases are formed without fp64 arithmetic (sincos_phase_df / _q30)
     __shared__ float2 s_w[IPN_MAX_J];
     __shared__ PhiTabEntry s_tab[tc::PP == 4 ? kPhiTabSize : 1];
+    __shared__ unsigned int s_wmax;  // bits of max_j |omega_j / 2 pi| (fp32 hi part)
+    if (threadIdx.x == 0) s_wmax = 0u;
+    __syncthreads();
     for (int j = threadIdx.x; j < J; j += 256) {
         const double wt = omega[s * J + j] * 0.15915494309189534561;
         const float wh = (float)wt;
         s_w[j] = make_float2(wh, (float)(wt - (double)wh));
+        atomicMax(&s_wmax, (unsigned)__float_as_int(fabsf(wh)));
     }
     if (tc::PP == 4)
         for (int k = threadIdx.x; k < kPhiTabSize; k += 256) s_tab[k] = phitab[k];
     __syncthreads();
-    for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
-        alignas(16) int8_t d[tc::PP][16];
+    const float wmax = __int_as_float((int)s_wmax);
+    const DrawConst dcs = dc[s];
+    for (int bt = blockIdx.x * PIMG_TILES; bt < n_bt && bt < (blockIdx.x + 1) * PIMG_TILES; ++bt) {
+        const int64_t pos = (int64_t)bt * tc::TN + row;
+        const bool valid = pos < T;
+        const int64_t i = valid ? perm[pos] : 0;
+        const double t = valid ? time[i] : 0.0;
+        const float th = (float)t, tl = (float)(t - (double)(float)t);
+        uint8_t* img = Pimg + ((int64_t)sl * n_bt + bt) * b_bytes;
+        if (tc::PP == 4) {
+            // every phase of this bin within the fp32 reduction's range (|turns| < 2^22, with a margin for the rounding of the
+            // product)?  Then the eight pairs of a chunk are straight-line code; the float64 route stays out of the loop.
+            const bool bounded = fabsf(th) * wmax < 4.0e6f;
+            for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
+                if (bounded)
+                    pimg_chunk_q30<true>(kc, J, valid, th, tl, t, s_w, s_tab, omega + s * J, img, b_plane, row);
+                else
+                    pimg_chunk_q30<false>(kc, J, valid, th, tl, t, s_w, s_tab, omega + s * J, img, b_plane, row);
+            }
+        } else {
+            for (int kc = kg; kc < Kpad / 16; kc += 256 / tc::TN) {
+                alignas(16) int8_t d[tc::PP][16];
 #pragma unroll
-        for (int kk = 0; kk < 16; kk += 2) {
-            const int k = kc * 16 + kk;
-            int q0 = 0, q1 = 0;
-            if (tc::PP == 4) {
-                if (valid) {
-                    if (k < 2 * J) {
-                        const float2 w = s_w[k >> 1];
-                        if (!sincos_phase_q30(w.x, w.y, th, tl, s_tab, q1, q0)) {
-                            double sn, cn;
-                            sincos(omega[s * J + (k >> 1)] * t, &sn, &cn);
-                            q0 = (int)llrint(cn * 1073741824.0);
-                            q1 = (int)llrint(sn * 1073741824.0);
+                for (int kk = 0; kk < 16; kk += 2) {
+                    const int k = kc * 16 + kk;
+                    int q0 = 0, q1 = 0;
+                    if (valid) {
+                        if (k < 2 * J) {
+                            float sn, cn;
+                            const float2 w = s_w[k >> 1];
+                            if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
+                            q0 = __float2int_rn(cn * 4194304.0f);  // cos row
+                            q1 = __float2int_rn(sn * 4194304.0f);  // sin row
+                        } else {
+                            q0 = q1 = 4194304;  // constant rows: Phi = 1
                         }
-                    } else {
-                        q0 = q1 = 1073741824;  // constant rows: Phi = 1
                     }
+                    int8_t dummy;
+                    split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
+                    split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
                 }
-                split_digits4(q0, d[0][kk], d[1][kk], d[2][kk], d[tc::PP - 1][kk]);
-                split_digits4(q1, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1], d[tc::PP - 1][kk + 1]);
-            } else {
-                if (valid) {
-                    if (k < 2 * J) {
-                        float sn, cn;
-                        const float2 w = s_w[k >> 1];
-                        if (!sincos_phase_df(w.x, w.y, th, tl, sn, cn)) sincos_phase(omega[s * J + (k >> 1)] * t, sn, cn);
-                        q0 = __float2int_rn(cn * 4194304.0f);  // cos row
-                        q1 = __float2int_rn(sn * 4194304.0f);  // sin row
-                    } else {
-                        q0 = q1 = 4194304;  // constant rows: Phi = 1
-                    }
-                }
-                int8_t dummy;
-                split_digits4(q0, dummy, d[0][kk], d[1][kk], d[2][kk]);
-                split_digits4(q1, dummy, d[0][kk + 1], d[1][kk + 1], d[2][kk + 1]);
+#pragma unroll
+                for (int pl = 0; pl < tc::PP; ++pl)
+                    *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
+                        *reinterpret_cast<const int4*>(d[pl]);
             }
         }
-#pragma unroll
-        for (int pl = 0; pl < tc::PP; ++pl)
-            *reinterpret_cast<int4*>(img + (size_t)pl * b_plane + ((size_t)kc * tc::TN + row) * 16) =
-                *reinterpret_cast<const int4*>(d[pl]);
-    }
-    if (kg == 0) {
-        const DrawConst dcs = dc[s];
-        const bool src = isfinite(dcs.c_hi);  // amp == 0: the likelihood is the constant C_s, every term is zero
-        const double kap = (valid && src) ? exposure[i] * dcs.kap : 0.0;
-        const float khi = (float)kap;
-        float4 c;
-        c.x = (valid && src) ? (float)counts[i] : 0.0f;
-        c.y = khi;
-        c.z = (float)(kap - (double)khi);
-        c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
-        *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
-        if (row == 0) {
-            float4 f;
-            // the tile holds at least one bin with counts: its first bin does (tiles are homogeneous up to the one boundary tile,
-            // which starts with the last bins with counts; the thread of row 0 is here and has the tile's first bin in i)
-            f.x = (valid && counts[i] > 0) ? 1.0f : 0.0f;
-            f.y = f.z = f.w = 0.0f;
-            *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
+        if (kg == 0) {
+            const bool src = isfinite(dcs.c_hi);  // amp == 0: the likelihood is the constant C_s, every term is zero
+            const double kap = (valid && src) ? exposure[i] * dcs.kap : 0.0;
+            const float khi = (float)kap;
+            float4 c;
+            c.x = (valid && src) ? (float)counts[i] : 0.0f;
+            c.y = khi;
+            c.z = (float)(kap - (double)khi);
+            c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
+            *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
+            if (row == 0) {
+                float4 f;
+                // the tile holds at least one bin with counts: its first bin does (tiles are homogeneous up to the one boundary
+                // tile, which starts with the last bins with counts; the thread of row 0 is here and has the tile's first bin in i)
+                f.x = (valid && counts[i] > 0) ? 1.0f : 0.0f;
+                f.y = f.z = f.w = 0.0f;
+                *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
+            }
         }
     }
 }

@@ -51,6 +51,12 @@ static inline int __float_as_int(float f) {
     return i;
 }
 static inline int __float2int_rn(float x) { return (int)std::nearbyintf(x); }
+// every CUDA thread is an OS thread here: shared-memory atomics must be real ones
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 using std::isfinite;
 template <class T>
 static inline T min(T a, T b) { return b < a ? b : a; }

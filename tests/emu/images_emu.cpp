@@ -61,7 +61,7 @@ int main(int argc, char** argv) {
     std::vector<PhiTabEntry> phitab(kPhiTabSize);
     shim::launch(tc_phitab_kernel, kPhiTabSize / 256, 256, phitab.data());
     if (n_bt > 0)
-        shim::launch3(tc_pimg_kernel, Dim3{(unsigned)n_bt, 1, 1}, 256, (int64_t)0, (int)J, Kpad, T, time.data(), expo.data(),
+        shim::launch3(tc_pimg_kernel, Dim3{(unsigned)((n_bt + PIMG_TILES - 1) / PIMG_TILES), 1, 1}, 256, (int64_t)0, (int)J, Kpad, T, time.data(), expo.data(),
                       counts.data(), perm.data(), flags, omega.data(), &dc, &td, (const PhiTabEntry*)phitab.data(), n_bt, b_bytes,
                       b_plane, Pp);
 
