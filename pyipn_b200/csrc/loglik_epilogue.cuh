@@ -82,15 +82,18 @@ __device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (
 
 // Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
 // not the exponent or the logarithm but three roundings of O(n)-sized quantities: n*y0, kappa*u and their difference
-// (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of eight such terms.  Here the two products and the
-// difference are formed as fp32 double-floats (exact FMA error terms, TwoSum), the small parts go to the `slo` sum, and
-// every term takes its own Kahan step.  ~11 more instructions per (delay, bin); remaining error ~3.7e-8 sqrt(sum n_i^2)
+// (6e-8 |v| each, |v| ~ n), and the uncompensated pairwise sum of such terms.  Here the two products are formed as fp32
+// double-floats (exact FMA error terms), the small parts go to the `slo` sum, and every product takes its own Kahan step.  ~11 more instructions per (delay, bin); remaining error ~3.7e-8 sqrt(sum n_i^2)
 // nats rms (measured: 1e-3 max at sum n_i^2 = 1.1e8) from the 2^(-y0) refinement of the logarithm, hence the hand-over to
 // the fp64 epilogue at sum n_i^2 = 4e7.
+// The two products are NOT subtracted from one another per bin: n y0 goes into one Kahan sum (ssum, scomp), kappa u into a
+// second one (qsum, qcomp), and only their rounding errors (exact, by FMA) and the small corrections meet in `slo`.  That saves
+// the TwoSum of the difference (3 instructions per bin less than summing d = n y0 - kappa u with one Kahan step) and gives
+// two independent dependency chains.  The caller forms (ssum - scomp) - (qsum - qcomp) + slo in float64 per work item.
 template <bool HC>
 __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
                                                 const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                                float mks8, float& ssum, float& scomp, float& slo) {
+                                                float mks8, float& ssum, float& scomp, float& qsum, float& qcomp, float& slo) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
@@ -101,8 +104,13 @@ __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&
         const float u = exp2_hilo_df(xh, xl, ul);
         // kappa u = q + (eq + klo u + khi ul), q = fl(khi u)
         const float q = c.y * u;
-        float small = fmaf(c.y, ul, fmaf(c.z, u, fmaf(c.y, u, -q)));
-        float d = -q;
+        const float qe = fmaf(c.y, ul, fmaf(c.z, u, fmaf(c.y, u, -q)));
+        {
+            const float yk = q - qcomp;  // Kahan step of the kappa u sum
+            const float tt = qsum + yk;
+            qcomp = (tt - qsum) - yk;
+            qsum = tt;
+        }
         if (HC) {
             const float w = 1.0f + u;
             const float ew = (u - (w - 1.0f)) + ul;
@@ -113,18 +121,14 @@ __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&
             // n log2(1 + u) = pr + (epr + nl r), pr = fl(n y0)
             const float pr = c.x * y0;
             const float epr = fmaf(c.x, y0, -pr);
-            d = pr - q;  // TwoSum(pr, -q)
-            const float bb = d - pr;
-            const float e1 = (pr - (d - bb)) + (-q - bb);
-            small = (fmaf(c.w, r, epr) + e1) - small;
+            slo += fmaf(c.w, r, epr) - qe;
+            const float yk = pr - scomp;  // Kahan step of the n y0 sum
+            const float tt = ssum + yk;
+            scomp = (tt - ssum) - yk;
+            ssum = tt;
         } else {
-            small = -small;
+            slo -= qe;
         }
-        slo += small;
-        const float yk = d - scomp;  // Kahan step per term
-        const float tt = ssum + yk;
-        scomp = (tt - ssum) - yk;
-        ssum = tt;
     }
 }
 

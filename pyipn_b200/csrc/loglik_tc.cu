@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
+            float qsum = 0.0f, qcomp = 0.0f;  // compensated epilogue: the kappa u sum (the n y0 sum is in ssum / scomp)
             double hacc = 0.0;
             const double ksd = (double)ks;
             const double sgn = MODE == EPI_STORE ? p.sgn[sl] : 0.0;
@@ -623,11 +624,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                             } else if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
                             else if (MODE == EPI_COMP && has_counts)
-                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, qsum, qcomp, slo);
                             else if (MODE == EPI_COMP && zero_plain)  // bins without counts: - kappa u is small unless the model is grossly off
                                 epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
-                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, qsum, qcomp, slo);
                             else if (has_counts)
                                 epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
                             else
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 }
             }
             if (MODE != EPI_STORE) {
-                double acc = ((double)ssum - (double)scomp) + (double)slo + hacc;
+                double acc = ((double)ssum - (double)scomp) - ((double)qsum - (double)qcomp) + (double)slo + hacc;
                 const int64_t g = (int64_t)dt * TM + quarter * 32 + lane;
                 if (g < p.G) atomicAdd(p.R + (int64_t)sl * p.Gpad + g, acc);
             }

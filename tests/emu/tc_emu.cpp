@@ -371,6 +371,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
             const int bt0 = chunk * tiles_per_chunk, bt1 = std::min(n_bt, bt0 + tiles_per_chunk);
             // per item: one (ssum, scomp, slo) per epilogue warp of the lane quarter (slot), for each fp32 mode
             float ssum[2][cfg::EPI_SLOTS] = {}, scomp[2][cfg::EPI_SLOTS] = {}, slo[2][cfg::EPI_SLOTS] = {};
+            float qsum[cfg::EPI_SLOTS] = {}, qcomp[cfg::EPI_SLOTS] = {};  // compensated epilogue: the kappa u sum
             double hacc[cfg::EPI_SLOTS] = {};
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
@@ -410,7 +411,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                         const float4* cp = &cst[(size_t)bt * cfg::TN + o];
                         if (has_counts) {
                             epi_units8<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
-                            epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
+                            epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], qsum[slot], qcomp[slot], slo[1][slot]);
                         } else {
                             epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
                             // n_terms = 1 (TcDraw::pad bit 0): tiles without counts take the plain unit in the compensated epilogue too
@@ -422,6 +423,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
             }
             for (int s = 0; s < cfg::EPI_SLOTS; ++s) {
                 for (int m = 0; m < 2; ++m) R[m] += ((double)ssum[m][s] - (double)scomp[m][s]) + (double)slo[m][s];
+                R[1] -= (double)qsum[s] - (double)qcomp[s];
                 R[2] += hacc[s];
             }
         }
