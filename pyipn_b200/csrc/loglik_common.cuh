@@ -130,6 +130,47 @@ __device__ __forceinline__ float exp2_core_df(float xf, float t, float& lo) {
     return hi * sc;
 }
 
+// ---- exponent assembly of the tcgen05 epilogues in integers ----
+// x = ks [S2 + 2^-8 S3 + 2^-24 (256 S4 + S5)] with ks = 2^-(12 + e) a power of two: H = 256 S2 + S3 is an exact 32-bit
+// integer (|S2| < 2^20, |S3| < 2^22) and x = H 2^-sh + L ks 2^-24 with sh = 20 + e (14 ... 30: tc_draw_kernel keeps e in
+// [-6, 10]).  So the integer part of x is a rounding shift of H and the fraction one int -> float conversion: 9 instructions
+// (LEA, IADD, SHF, LEA, LEA, 2 I2FP, FMUL, FFMA) where the floating-point route needed 12 (two magic-number conversions,
+// three FFMA, five FADD for rint and the remainder), and the exponent goes into the result with one LEA as before.
+// Returns the fraction xf (|xf| <= 1/2 + |low levels|), k = the integer part.
+__device__ __forceinline__ float exponent_parts(int s2, int s3, int s4, int s5, int sh, float inv, float ks24, int& k) {
+    const int H = s2 * 256 + s3;
+    k = (H + (1 << (sh - 1))) >> sh;
+    const int fr = H - (k << sh);
+    return fmaf((float)(s4 * 256 + s5), ks24, (float)fr * inv);  // inv = 2^-sh
+}
+// e^(xf ln 2) 2^k, |xf| <= 0.54, |k| <= 120
+__device__ __forceinline__ float exp2_parts(float xf, int k) {
+    const float z = fmaf(xf, 0.693145751953125f, xf * 1.4286068203094172e-06f);
+    float p = fmaf(z, 0.00019602585234679282f, 0.0013943274971097708f);
+    p = fmaf(p, z, 0.008333928883075714f);
+    p = fmaf(p, z, 0.041666384786367416f);
+    p = fmaf(p, z, 0.166666641831398f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.0f);
+    p = fmaf(p, z, 1.0f);
+    return __int_as_float(__float_as_int(p) + (k << 23));
+}
+// ... as hi + lo (see exp2_core_df)
+__device__ __forceinline__ float exp2_parts_df(float xf, int k, float& lo) {
+    const float z = fmaf(xf, 0.693145751953125f, xf * 1.4286068203094172e-06f);
+    float p = fmaf(z, 0.00019602585234679282f, 0.0013943274971097708f);
+    p = fmaf(p, z, 0.008333928883075714f);
+    p = fmaf(p, z, 0.041666384786367416f);
+    p = fmaf(p, z, 0.166666641831398f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.0f);
+    const float hi = fmaf(p, z, 1.0f);
+    const float l = fmaf(p, z, 1.0f - hi);
+    const float sc = __int_as_float((k << 23) + 0x3f800000);
+    lo = l * sc;
+    return hi * sc;
+}
+
 __device__ __forceinline__ float exp2_poly(float x) {
     x = fminf(fmaxf(x, -125.0f), 127.0f);
     const float t = x + kMagic;

@@ -37,17 +37,15 @@ __device__ __forceinline__ int fold_level6(int s5, int s6) { return s5 + ((s6 + 
 // HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
 template <bool HC>
 __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                           const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                           float mks8, float& ssum, float& scomp, float& slo) {
+                                           const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp, float& slo) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
-        // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): S2 part exact (magic-number int->float inside the FMA)
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        const float u = exp2_hilo(xh, xl);
+        // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): integer part and fraction from the integers (exponent_parts)
+        int k;
+        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        const float u = exp2_parts(xf, k);
         if (HC) {
             float l;
             v[j] = poisson_term(u, c.x, c.w, c.y, c.z, l);
@@ -70,13 +68,12 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
 
 // Store epilogue (ipn_rff_eval on uniform bins through the same contraction): no Poisson terms, just u = 2^x of the eight bins.
 __device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                                 float ks, float ks8, float ks24, float mks, float mks8, float (&u)[8]) {
+                                                 int sh, float inv, float ks24, float (&u)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        u[j] = exp2_hilo(xh, xl);
+        int k;
+        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        u[j] = exp2_parts(xf, k);
     }
 }
 
@@ -92,16 +89,15 @@ __device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (
 // two independent dependency chains.  The caller forms (ssum - scomp) - (qsum - qcomp) + slo in float64 per work item.
 template <bool HC>
 __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                                const float4* __restrict__ cst, float ks, float ks8, float ks24, float mks,
-                                                float mks8, float& ssum, float& scomp, float& qsum, float& qcomp, float& slo) {
+                                                const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp,
+                                                float& qsum, float& qcomp, float& slo) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
-        const float xh = fmaf(__int_as_float(s2[j] + kMagicBits), ks, mks);
-        float xl = fmaf(__int_as_float(s3[j] + kMagicBits), ks8, mks8);
-        xl = fmaf((float)(s4[j] * 256 + s5[j]), ks24, xl);
-        float ul;  // u = 2^x as hi + lo (exp2_core_df)
-        const float u = exp2_hilo_df(xh, xl, ul);
+        int k;
+        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        float ul;  // u = 2^x as hi + lo
+        const float u = exp2_parts_df(xf, k, ul);
         // kappa u = q + (eq + klo u + khi ul), q = fl(khi u)
         const float q = c.y * u;
         const float qe = fmaf(c.y, ul, fmaf(c.z, u, fmaf(c.y, u, -q)));

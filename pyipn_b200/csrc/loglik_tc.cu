@@ -516,8 +516,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
             const int bt0 = chunk * p.tiles_per_chunk;
             const int bt1 = min(p.n_bt, bt0 + p.tiles_per_chunk);
             const float ks = p.td[sl].ks;
-            const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
-            const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
+            const float ks24 = ks * 5.9604644775390625e-8f;
+            // ks = 2^-(12 + e): the integer exponent assembly shifts by sh = 20 + e (exponent_parts, loglik_common.cuh)
+            const int sh = 8 - (((__float_as_int(ks) >> 23) & 0xff) - 127);
+            const float inv = ks * 0.00390625f;  // 2^-sh
             // Kahan pair + small-correction sum carried across the whole item; folded into fp64 once at the end
             float ssum = 0.0f, scomp = 0.0f, slo = 0.0f;
             float qsum = 0.0f, qcomp = 0.0f;  // compensated epilogue: the kappa u sum (the n y0 sum is in ssum / scomp)
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                         for (int h = 0; h < NH; ++h) {
                             if (MODE == EPI_STORE) {
                                 float u8[8];
-                                epi_units8_store(acc[h][0], acc[h][1], acc[h][2], acc[h][3], ks, ks8, ks24, mks, mks8, u8);
+                                epi_units8_store(acc[h][0], acc[h][1], acc[h][2], acc[h][3], sh, inv, ks24, u8);
                                 // bin i = p Q + q: p = the column's position among the "bins", q = this thread's "delay" row;
                                 // for one column the 32 lanes of the warp write 256 consecutive bytes
                                 const int64_t q = (int64_t)dt * TM + quarter * 32 + lane;
@@ -624,15 +626,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                             } else if (MODE == EPI_FP64)
                                 epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
                             else if (MODE == EPI_COMP && has_counts)
-                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, qsum, qcomp, slo);
+                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
                             else if (MODE == EPI_COMP && zero_plain)  // bins without counts: - kappa u is small unless the model is grossly off
-                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
-                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, qsum, qcomp, slo);
+                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
                             else if (has_counts)
-                                epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                                epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                             else
-                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ks, ks8, ks24, mks, mks8, ssum, scomp, slo);
+                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                         }
                     }
                     __syncwarp();

@@ -91,7 +91,7 @@ __global__ void tc_draw_kernel(int64_t S0, int Sb, int J, int n_crows, const dou
         sumw += wj;
     }
     const double c = fabs((double)dc[s].c_hi + (double)dc[s].c_lo);  // inf for amp == 0 (handled through the consts)
-    int e = 20;  // sigma = 2^e, start high and walk down
+    int e = 10;  // sigma = 2^e, start high and walk down (e in [-6, 10]: the epilogue's integer exponent assembly shifts by 20 + e)
     const double lim_c = (double)n_crows * (1.0 - 1e-6);
     while (e > -6 && (ldexp(mx, e) > 1.0 || (isfinite(c) && ldexp(c, e) > lim_c))) --e;
     TcDraw t;

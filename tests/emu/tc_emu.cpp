@@ -211,7 +211,7 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
         sumw += wj;
     }
     const double cabs = std::fabs((double)dc.c_hi + (double)dc.c_lo);
-    int e = 20;
+    int e = 10;
     const double lim_c = (double)ncrow * (1.0 - 1e-6);
     while (e > -6 && (std::ldexp(mx, e) > 1.0 || (std::isfinite(cabs) && std::ldexp(cabs, e) > lim_c))) --e;
     const float sigma_f = (float)std::ldexp(1.0, e), ks = (float)std::ldexp(1.0, -12 - e);
@@ -293,8 +293,9 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
         cc.w = cc.x * 1.44269504f;
         cst[pos] = cc;
     }
-    const float ks8 = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
-    const float mks = -kMagic * ks, mks8 = -kMagic * ks8;
+    const float ks24 = ks * 5.9604644775390625e-8f;
+    const int sh = 8 - (((__float_as_int(ks) >> 23) & 0xff) - 127);
+    const float inv = ks * 0.00390625f;
     const double ksd = (double)ks, sigma = (double)sigma_f;
     const double cs = (double)dc.c_hi + (double)dc.c_lo;
 
@@ -410,12 +411,12 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                         }
                         const float4* cp = &cst[(size_t)bt * cfg::TN + o];
                         if (has_counts) {
-                            epi_units8<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
-                            epi_units8_comp<true>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], qsum[slot], qcomp[slot], slo[1][slot]);
+                            epi_units8<true>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[0][slot], scomp[0][slot], slo[0][slot]);
+                            epi_units8_comp<true>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[1][slot], scomp[1][slot], qsum[slot], qcomp[slot], slo[1][slot]);
                         } else {
-                            epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[0][slot], scomp[0][slot], slo[0][slot]);
+                            epi_units8<false>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[0][slot], scomp[0][slot], slo[0][slot]);
                             // n_terms = 1 (TcDraw::pad bit 0): tiles without counts take the plain unit in the compensated epilogue too
-                            epi_units8<false>(t2, t3, t4, t5, cp, ks, ks8, ks24, mks, mks8, ssum[1][slot], scomp[1][slot], slo[1][slot]);
+                            epi_units8<false>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[1][slot], scomp[1][slot], slo[1][slot]);
                         }
                         epi_units8_hifi(t2, t3, t4, t5, cp, ksd, hacc[slot]);
                     }

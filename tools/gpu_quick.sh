@@ -2,6 +2,7 @@
 mkdir -p gpurun_out/r2s16; O=gpurun_out/r2s16
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.txt
 timeout 300 python bench.py --draws 500 --steps 3 --warmup 2 --no-cpu-baseline > $O/bench_500.json 2> $O/bench_500.err; echo "bench rc=$?"
+timeout 300 python bench.py --workload config4 --steps 3 --warmup 2 > $O/bench_c4.json 2> $O/bench_c4.err; echo "c4 rc=$?"; python -c "import json; j=json.loads(open(\"$O/bench_c4.json\").read().strip().splitlines()[-1]); print(\"config4\", j[\"ms_per_step\"], j[\"parity\"][\"max_abs_nats\"])"
 timeout 300 python bench.py --workload rff_eval --steps 5 --warmup 3 > $O/bench_rff.json 2> $O/bench_rff.err; echo "rff rc=$?"
 python - <<'PY'
 import json
