@@ -427,4 +427,7 @@ def test_large_shapes_vs_oracle(ctx, T, G, S):
     idx = np.unique(np.clip([0, best - 1, best, best + 1, G // 3, G - 2, G - 1], 0, G - 1))
     exp = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"][idx])
     assert np.abs(ll[idx] - exp).max() < ATOL
-    assert idx[int(np.argmax(exp[:, 0]))] == best
+    # the device's arg-max is the oracle's, unless the grid is so fine (70 001 delays: 1.4e-5 s apart) that the oracle's best
+    # points are closer together than the tolerance -- then it must be one of those
+    e0 = exp[:, 0]
+    assert idx[int(np.argmax(e0))] == best or e0[list(idx).index(best)] > e0.max() - ATOL
