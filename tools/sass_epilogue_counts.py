@@ -3,7 +3,8 @@
 The tcgen05 likelihood kernel is bound by the issue slots of its epilogue, so instructions per
 (delay, bin) is the number to watch when the epilogue changes.  This walks `cuobjdump -sass` of
 pyipn_b200/csrc/build/loglik_tc.o, cuts every `loglik_tc_kernel<7, MODE>` at its branch instructions and reports the
-straight-line blocks that hold an 8-bin epilogue unit (recognised by their 96 FFMA of exponent assembly + 2^x), with the
+straight-line blocks that hold an 8-bin epilogue unit (recognised by the 16 int -> float conversions of the exponent assembly
+and the 64+ FFMA of the polynomials), with the
 opcode histogram that tells the variants apart (MUFU.LG2 = per-bin logarithm, DFMA = product epilogue, DADD/DMUL = fp64).
 
     python tools/sass_epilogue_counts.py [--md]
@@ -64,7 +65,8 @@ def main():
         seen = set()
         for b in bl:
             h = collections.Counter(op.split(".")[0] for op in b)
-            if h.get("FFMA", 0) < 90 or len(b) > 700:
+            # an 8-bin unit: eight I2FP pairs of the integer exponent assembly (16 conversions) and eight polynomials (>= 64 FFMA)
+            if h.get("I2FP", 0) < 16 or h.get("FFMA", 0) < 64 or len(b) > 700:
                 continue
             kind, h = describe(b)
             key = (kind, len(b))
