@@ -200,3 +200,34 @@ def test_rff_eval_odd_number_of_frequencies(ctx, J, uniform):
     assert ctx.last_rff_impl == (2 if uniform else 1)
     for s in range(S):
         np.testing.assert_allclose(got[s], amp[s] * np.exp(orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])), rtol=RTOL)
+
+
+def test_rff_eval_contraction_across_draw_batches(ctx):
+    """The contraction route works through the draws in internal batches like the likelihood grid: with IPN_OPT_DRAW_BATCH = 2 and
+    five draws -- one of them with amplitudes beyond the 2^120 exponent bound, which the direct kernel takes over inside ITS
+    batch -- every draw must match the oracle and the un-batched call."""
+    from pyipn_b200._lib import OPT_DRAW_BATCH
+
+    rng = np.random.default_rng(11)
+    T, S, J = 4099, 5, 100
+    time = 3.0 + 0.002 * (np.arange(T) + 0.5)
+    omega = rng.normal(size=(S, J)) * 1.5
+    a = rng.normal(size=(S, J)) * 0.12
+    b = rng.normal(size=(S, J)) * 0.12
+    a[3] *= 12.0  # sum_j |(a_j, b_j)| log2e > 120: unbounded exponent -> direct kernel for this draw only
+    b[3] *= 12.0
+    shift, amp = rng.normal(size=S), np.exp(rng.normal(size=S))
+    whole = ctx.rff_eval(time, omega, a, b, shift, amp)
+    assert ctx.last_rff_impl == 2
+    ctx.set_option(OPT_DRAW_BATCH, 2)
+    try:
+        got = ctx.rff_eval(time, omega, a, b, shift, amp)
+        assert ctx.last_rff_impl == 2 and ctx.last_draw_batch == 2
+    finally:
+        ctx.set_option(OPT_DRAW_BATCH, 0)
+    np.testing.assert_array_equal(got, whole)
+    for s in range(S):
+        logf = orc.log_intensity_folded(time - shift[s], omega[s], a[s], b[s])
+        keep = np.abs(logf) < 600.0
+        np.testing.assert_allclose(got[s][keep], amp[s] * np.exp(logf[keep]), rtol=RTOL)
+    assert (1.44269504 * np.sqrt(a[3] ** 2 + b[3] ** 2).sum()) > 120.0
