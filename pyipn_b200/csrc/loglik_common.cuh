@@ -137,11 +137,14 @@ __device__ __forceinline__ float exp2_core_df(float xf, float t, float& lo) {
 // (LEA, IADD, SHF, LEA, LEA, 2 I2FP, FMUL, FFMA) where the floating-point route needed 12 (two magic-number conversions,
 // three FFMA, five FADD for rint and the remainder), and the exponent goes into the result with one LEA as before.
 // Returns the fraction xf (|xf| <= 1/2 + |low levels|), k = the integer part.
+// kLevel6Half: S5 arrives with the level-6 sum folded in by an arithmetic shift (fold_level6, loglik_epilogue.cuh), i.e. half a
+// level-5 unit too low on average; the half goes back in through the addend of the conversion's FMA (no extra instruction).
+constexpr float kLevel6Half = 0.5f;
 __device__ __forceinline__ float exponent_parts(int s2, int s3, int s4, int s5, int sh, float inv, float ks24, int& k) {
     const int H = s2 * 256 + s3;
     k = (H + (1 << (sh - 1))) >> sh;
     const int fr = H - (k << sh);
-    return fmaf((float)(s4 * 256 + s5), ks24, (float)fr * inv);  // inv = 2^-sh
+    return fmaf((float)(s4 * 256 + s5), ks24, fmaf((float)fr, inv, kLevel6Half * ks24));  // inv = 2^-sh
 }
 // e^(xf ln 2) 2^k, |xf| <= 0.54, |k| <= 120
 __device__ __forceinline__ float exp2_parts(float xf, int k) {

@@ -29,9 +29,11 @@ __device__ __forceinline__ void split_digits5(long long q, int8_t& d1, int8_t& d
     split_digits4((int)r, d1, d2, d3, d4);
 }
 
-// The level-6 sum (W's fifth digit times Phi's first, weight 2^-8 of level 5) rounded into level-5 units: what the epilogue
-// threads do with the fifth accumulator right after loading it (two integer instructions per bin)
-__device__ __forceinline__ int fold_level6(int s5, int s6) { return s5 + ((s6 + 128) >> 8); }
+// The level-6 sum (W's fifth digit times Phi's first and W's fourth times Phi's second, weight 2^-8 of level 5) brought into
+// level-5 units right after the epilogue threads have loaded it: an arithmetic shift, i.e. rounded DOWN -- the half unit this
+// loses on average is added back where the low levels are converted (kLevel6Half in exponent_parts and in the fp64 epilogue), so
+// the fold costs two integer instructions per bin and leaves a zero-mean error of 2^-37 / sigma in x.
+__device__ __forceinline__ int fold_level6(int s5, int s6) { return s5 + (s6 >> 8); }
 
 // Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, compensated sum.
 // HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
@@ -136,7 +138,7 @@ __device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];
         const double x = ksd * ((double)s2[j] + 0.00390625 * (double)s3[j] +
-                                5.9604644775390625e-8 * ((double)s4[j] * 256.0 + (double)s5[j]));
+                                5.9604644775390625e-8 * ((double)s4[j] * 256.0 + (double)s5[j] + (double)kLevel6Half));
         const double u = exp2(x);
         const double kap = (double)c.y + (double)c.z;
         acc += (double)c.x * (log1p(u) * kLog2e) - kap * u;
