@@ -24,16 +24,19 @@
 // Mapping: MMA M = 128 trial delays, N = 32 time bins, K = 32 per UTCIMMA.  The first four W digits of a work item
 // (draw, 128 delays) are staged once through shared memory into TENSOR MEMORY (tcgen05.cp, 224 columns, two planes at a
 // time) and used as the A operand from there; the fifth digit plane stays in shared memory for the item (one product, SS
-// form).  Why tensor memory: with both operands in shared memory the 63 MMAs of a tile would re-read
-// the 128-row A operand every time (6 KB per 32-cycle MMA = 192 B/clk, more than shared memory delivers; measured
-// ~75 cycles per MMA).  The Phi digits (B operand, 21 KB per tile) stream through a 4-stage bulk-copy ring, the
+// form).  Why tensor memory: with both operands in shared memory every MMA re-reads the 128-row A operand (4 KB + 1 KB of B
+// per MMA at 128 B/clk: measured 43 cycles against 18 with A in tensor memory).  The Phi digits (B operand, 28 KB per tile)
+// stream through a 4-stage bulk-copy ring, the
 // tiles' Poisson constants through a separate 6-deep ring.  4 level accumulators x 32 columns x 2 buffers sit in
-// TMEM columns [256, 512), the level-6 accumulator single-buffered in the 32 columns left, [224, 256).  An epilogue thread owns ONE delay (TMEM lane) and walks the tile's bins (columns): a
-// bin's counts/kappa are warp-uniform, bins are pre-sorted so that tiles without counts skip the log entirely,
-// and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile atomics.
+// TMEM columns [256, 512), the level-6 accumulator single-buffered in the 32 columns left, [224, 256).  An epilogue thread
+// owns ONE delay (TMEM lane) and walks the tile's bins (columns): a bin's counts / kappa are warp-uniform, bins are
+// partitioned so that tiles are homogeneous and tiles without counts skip the log entirely (and the two kinds of tile
+// are interleaved, tc_bin_position), and the sum over bins is a per-thread compensated sum -- no shuffles, no per-tile
+// atomics.
 // Warp roles: 0..15 = epilogue, 16 = bulk-copy producer, 17 / 18 = MMA issuers of the even / odd tiles (17 also does the
 // tcgen05.cp of the W digits).  Three instantiations by epilogue arithmetic (plain fp32 / compensated fp32 / fp64), each
-// working on the draws whose brightness asks for it (tc_draw_kernel decides per draw).
+// working on the draws whose brightness asks for it (tc_draw_kernel decides per draw), and a fourth with
+// a store epilogue, which turns the same contraction into ipn_rff_eval on uniform bins (run_rff_eval_tc below).
 // Experiment / test hooks (IPN_TC_DEBUG wait-cycle counters, IPN_TC_SKIP_MATH, IPN_TC_SKIP_MMA, IPN_TC_ONE_ISSUER,
 // IPN_TC_EPI_DELAY, IPN_TC_GRID, IPN_TC_CHUNK_TILES) exist only in a build with -DIPN_TC_HOOKS (libipn_b200_hooks.so, which
 // tests/test_gpu_loglik.py and tools/ load to check that results do not depend on pacing): the shipped library contains
