@@ -64,6 +64,8 @@ struct ipn_ctx {
     int64_t draw_batch = 0;
     int rff_impl = 0;   // ipn_rff_eval: 0 auto, 1 direct kernel, 2 tcgen05 contraction (uniform bins guaranteed by the caller)
     int last_rff_impl = 0;
+    bool tc_attr_set[8][4] = {};  // tcgen05 path: shared-memory attribute set on this device for (K steps, epilogue mode)
+    bool tc_trap_set = false;     // ... and the time-out record's address published to the device code
     int n_terms = 1;    // how many likelihood passes are summed into the caller's result (sky grid: D detectors): the 1e-3 nat
                         // tolerance is shared between them, so the per-draw epilogue choice is made for a 1 / n_terms share
     // scratch

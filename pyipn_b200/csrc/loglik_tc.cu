@@ -292,6 +292,22 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     // uniform datapath: UTCIMMA takes its descriptors from uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    constexpr int DRAW_MODE = MODE == EPI_STORE ? (int)EPI_FP32 : MODE;  // which draws (TcDraw::hifi) this instantiation works on
+
+    // In automatic mode every instantiation is launched and the draws' modes are only known on the device: leave at once --
+    // before barriers, tensor-memory allocation and the role loops -- if no draw of the batch is ours (a single-draw grid is
+    // ~1 ms of work, and two empty instantiations that set everything up and tore it down again were 3 % of it).
+    {
+        __shared__ int s_any;
+        if (warp == 0) {
+            int any = 0;
+            for (int i = lane; i < p.Sb; i += 32) any |= p.td[i].hifi == DRAW_MODE;
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0) s_any = any;
+        }
+        __syncthreads();
+        if (!s_any) return;
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -321,7 +337,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    constexpr int DRAW_MODE = MODE == EPI_STORE ? (int)EPI_FP32 : MODE;  // which draws (TcDraw::hifi) this instantiation works on
     const int items_per_draw = p.nchunk * p.n_dt;
     const int64_t n_items = (int64_t)p.Sb * items_per_draw;
 
@@ -766,12 +781,18 @@ static int run_tc_grid(ipn_ctx* ctx, int64_t T, const double* time, const double
     // (a draw whose exponent is not bounded goes to the fp64 epilogue whatever the option says, so that one always runs)
     const int hm = ctx->hifi_mode;
     const bool run_mode[N_EPI + 1] = {!st && (hm == 0 || hm == 2), !st && (hm == 0 || hm == 3), !st, st != nullptr};
-    {
+    // once per context (= per device): the time-out record's address, and the shared-memory attribute of every instantiation
+    // that runs (a single-draw grid is ~1 ms of device work: a dozen microseconds of driver calls per launch set show)
+    if (!ctx->tc_trap_set) {
         int* trap = trap_record_device_ptr();
         IPN_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trap_record, &trap, sizeof(trap), 0, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->tc_trap_set = true;
     }
     for (int m = 0; m <= N_EPI; ++m)
-        if (run_mode[m]) IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (run_mode[m] && !ctx->tc_attr_set[ksteps][m]) {
+            IPN_CUDA_CHECK(cudaFuncSetAttribute(kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->tc_attr_set[ksteps][m] = true;
+        }
 
     for (int64_t S0 = 0; S0 < S; S0 += Sbatch) {
         const int Sb = (int)((S - S0 < Sbatch) ? (S - S0) : Sbatch);
