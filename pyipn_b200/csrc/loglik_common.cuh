@@ -144,7 +144,10 @@ __device__ __forceinline__ float exponent_parts(int s2, int s3, int s4, int s5, 
     const int H = s2 * 256 + s3;
     k = (H + (1 << (sh - 1))) >> sh;
     const int fr = H - (k << sh);
-    return fmaf((float)(s4 * 256 + s5), ks24, fmaf((float)fr, inv, kLevel6Half * ks24));  // inv = 2^-sh
+    // the half unit rides in the FMA of the LOW levels: their product has a full mantissa of pseudo-random bits, so the tiny
+    // addend survives the rounding on average; behind the exact fr 2^-sh (few significant bits) it would be rounded away every
+    // time (measured in the emulation: a bias of -0.5 ks 2^-24 in x)
+    return fmaf((float)fr, inv, fmaf((float)(s4 * 256 + s5), ks24, kLevel6Half * ks24));  // inv = 2^-sh
 }
 // e^(xf ln 2) 2^k, |xf| <= 0.54, |k| <= 120
 __device__ __forceinline__ float exp2_parts(float xf, int k) {

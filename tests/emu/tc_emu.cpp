@@ -133,7 +133,55 @@ static int run_funcs() {
         const float y0 = poisson_term(u, 1.0f, 1.44269504f, 0.0f, 0.0f, lo);
         e_tiny.add(((double)y0 + (double)lo) / ((double)u * 1.4426950408889634) - 1.0);
     }
+    // integer exponent assembly + 2^x from parts (the fp32 epilogues' route), on random level sums
+    Stat e_parts, e_parts_df;
+    long digit_mismatch = 0, position_errors = 0;
+    for (int i = 0; i < N; ++i) {
+        const int sh = 17 + (int)(rng() % 8);                            // 17 .. 24: sigma = 2^-3 .. 2^4 (prior draws: 2^-1 .. 2^1)
+        const float ks = std::ldexp(1.0f, 8 - sh), inv = ks * 0.00390625f, ks24 = ks * 5.9604644775390625e-8f;
+        const double xr = unif(-40.0, 40.0);                             // target exponent
+        long long h = std::llrint(std::ldexp(xr, sh));                   // H = 256 S2 + S3
+        if (h > 230000000ll) h = 230000000ll;
+        if (h < -230000000ll) h = -230000000ll;
+        const int s3 = (int)(rng() % 2000001) - 1000000, s2 = (int)((h - s3) / 256);
+        // the low levels as the kernel sees them: |ks 2^-24 (256 S4 + S5)| stays below a few hundredths for every draw the fp32
+        // epilogues take (bounded exponent), and |S4| < 7.4e6, |S5| < 1.2e7 by the digit ranges
+        double lt = unif(-0.04, 0.04) / (double)ks24;
+        if (lt > 1.8e9) lt = 1.8e9;
+        if (lt < -1.8e9) lt = -1.8e9;
+        const int s5 = (int)(rng() % 2000001) - 1000000, s4 = (int)((lt - s5) / 256.0);
+        const double x = (double)ks * ((double)s2 + (double)s3 / 256.0 + ((double)s4 * 256.0 + (double)s5 + 0.5) / 16777216.0);
+        if (std::fabs(x) > 100.0) continue;
+        int k;
+        const float xf = exponent_parts(s2, s3, s4, s5, sh, inv, ks24, k);
+        e_parts.add((double)exp2_parts(xf, k) / std::exp2(x) - 1.0);
+        float lo;
+        const float hi = exp2_parts_df(xf, k, lo);
+        e_parts_df.add(((double)hi + (double)lo) / std::exp2(x) - 1.0);
+        // packed digit split against the one-at-a-time split
+        const int q = (int)(rng() % 2147483647u) - 1073741824;
+        int8_t d1, d2, d3, d4;
+        split_digits4(q, d1, d2, d3, d4);
+        const unsigned w = pack_digits4(q);
+        digit_mismatch += (int8_t)(w >> 24) != d1 || (int8_t)(w >> 16) != d2 || (int8_t)(w >> 8) != d3 || (int8_t)w != d4;
+    }
+    // the interleaved bin order is a permutation of [0, T) for any split of T bins into the two classes
+    for (int it = 0; it < 400; ++it) {
+        const long long T = 1 + (long long)(rng() % 5000), n_nz = (long long)(rng() % (T + 1));
+        std::vector<char> hit((size_t)T, 0);
+        for (long long r = 0; r < n_nz; ++r) {
+            const long long p = tc_bin_position(true, r, n_nz, T, 32);
+            if (p < 0 || p >= T || hit[(size_t)p]++) ++position_errors;
+        }
+        for (long long r = 0; r < T - n_nz; ++r) {
+            const long long p = tc_bin_position(false, r, n_nz, T, 32);
+            if (p < 0 || p >= T || hit[(size_t)p]++) ++position_errors;
+        }
+    }
     std::printf("{\n");
+    std::printf("\"digit_pack_mismatches\": %ld,\n\"bin_position_errors\": %ld,\n", digit_mismatch, position_errors);
+    e_parts.print("exp2_parts_rel");
+    e_parts_df.print("exp2_parts_df_rel");
     e_poly.print("exp2_poly_rel");
     e_hilo.print("exp2_hilo_rel");
     e_sin.print("sin_phase_abs");

@@ -69,6 +69,16 @@ def test_function_error_statistics(emu):
     for key in ("log2_1pu_abs_mufu_like", "log2_1pu_abs_bad_seed"):
         assert abs(st[key]["mean"]) < 5e-10 and st[key]["rms"] < 4e-8, (key, st[key])
     assert st["log2_1pu_tiny_rel"]["max"] < 2e-7, st["log2_1pu_tiny_rel"]
+    # round 2: sine / cosine of the Phi image directly in 2^-30 fixed point (1024-point table + first-order rotation), phases
+    # up to 1e5 rad: fifty times closer than the fp32 polynomial route
+    for key in ("sin_phase_q30_abs", "cos_phase_q30_abs"):
+        assert abs(st[key]["mean"]) < 2e-11 and st[key]["rms"] < 5e-10 and st[key]["max"] < 3e-9, (key, st[key])
+    # integer exponent assembly + 2^x from (fraction, integer part): unbiased like exp2_poly, and the hi + lo form of the
+    # compensated epilogue at less than half its random error
+    assert abs(st["exp2_parts_rel"]["mean"]) < 3e-10 and st["exp2_parts_rel"]["rms"] < 3.2e-8 and st["exp2_parts_rel"]["max"] < 1.3e-7
+    assert abs(st["exp2_parts_df_rel"]["mean"]) < 3e-10 and st["exp2_parts_df_rel"]["rms"] < 1.6e-8, st["exp2_parts_df_rel"]
+    # the packed digit split of the image kernel is the one-at-a-time split; the interleaved bin order is a permutation
+    assert st["digit_pack_mismatches"] == 0 and st["bin_position_errors"] == 0
 
 
 def test_config2_full_size_all_epilogues(emu, tmp_path):
