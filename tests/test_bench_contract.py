@@ -29,3 +29,35 @@ def test_reference_arm_nonzero_rank_is_silent():
                         "--warmup", "0", "--bins", "2000", "--delays", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT,
                        env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_parity_check_covers_every_batch_and_catches_an_error():
+    """bench.py's oracle check of the timed result: one draw of every internal draw batch of every rank is picked, an exact
+    result passes, and an error of 2e-3 nats at any picked pair fails the run (the function is pure host code)."""
+    import types
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import c_oracle as corc
+    from pyipn_b200.distributed import shard_bounds
+    from pyipn_b200.synth import delay_grid_workload
+
+    S, world, batch = 23, 2, 3
+    w = delay_grid_workload(T=1500, G=48, S=S, dt_bin=0.01)
+    full = corc.loglik_delay_grid(w["counts"], w["time"], w["exposure"], w["omega"], w["a"], w["b"], w["amp"], w["bkg"], w["delays"])
+    a = types.SimpleNamespace(parity_draws=64)
+    p = bench.parity_check(a, w, full.copy(), S, world, batch)
+    assert p["ok"] and p["max_abs_nats"] < 1e-9 and p["argmax_equal"]
+    n_batches = sum(-(-(shard_bounds(S, r, world)[1] - shard_bounds(S, r, world)[0]) // batch) for r in range(world))
+    assert p["draw_batches_of_the_library"] == n_batches and p["draws_checked"] >= n_batches
+    # every batch of every rank holds at least one checked draw: an error in ANY batch is seen
+    gsel = p["delays_checked"]
+    for r in range(world):
+        lo, hi = shard_bounds(S, r, world)
+        for b0 in range(lo, hi, batch):
+            bad = full.copy()
+            bad[gsel[0], b0:min(hi, b0 + batch)] += 2e-3
+            q = bench.parity_check(a, w, bad, S, world, batch)
+            assert not q["ok"] and q["max_abs_nats"] > 1.9e-3, (r, b0)
