@@ -40,17 +40,36 @@ struct TcDraw {
 // ---- order of the bins in the Phi image of the tcgen05 path ----
 // Bins with counts cost the epilogue 2.4x the instructions of bins without (the logarithm), and with twelve digit-plane products
 // a tile of either kind costs the tensor pipe the same: tiles WITH counts are epilogue-bound (the tensor pipe idles), tiles
-// WITHOUT are tensor-bound (the epilogue warps idle).  So the two kinds are interleaved: the bins are still partitioned (counts
-// first, original order within each class, so every 32-bin tile is homogeneous and a tile without counts skips the logarithm),
-// but the TILES are laid out  C Z Z C | C Z Z C | ...  (C: with counts, Z: without) while both kinds last -- any two
-// consecutive tiles hold one of each, and each of the four epilogue warps of a lane quarter, which take units of every other
-// tile, alternates between the kinds as well.  Only full tiles take part; what is left of the longer class follows in its
-// natural order (-DIPN_TC_INTERLEAVE=0: everything in natural order, the round-1 layout).
+// WITHOUT are tensor-bound (the epilogue warps idle).  So the two kinds are interleaved: the bins are partitioned (counts
+// first, original order within each class, so every 32-bin tile is homogeneous up to the one boundary tile), and the TILES
+// are laid out  C Z Z C | C Z Z C | ...  (C: with counts, Z: without) while both kinds last -- any two consecutive tiles hold
+// one of each, and each of the four epilogue warps of a lane quarter, which take units of every other tile, alternates between
+// the kinds as well.  Only full tiles take part; what is left of the longer class follows in its natural order.
+// The epilogue decides "logarithm or not" per 8-bin UNIT (the flag block of the Phi image holds one flag per 8 rows: the
+// unit's first bin holds counts -- within any 8 rows of any layout here the bins with counts come first).
+// Layouts that were measured against this one (tools/gpu_mixed.sh, profiles/r02_tile_layouts_ab.txt):
+//   -DIPN_TC_INTERLEAVE=0: everything in natural order (the round-1 layout): 2 % slower
+//   -DIPN_TC_INTERLEAVE=2: the kinds mixed WITHIN every tile while both last -- rows 0..15 of tile j hold the bins with counts
+//      of rank 16 j .. 16 j + 15, rows 16..31 the bins without counts of the same ranks, so every tile costs the epilogue the
+//      same: 4-6 % SLOWER.  Of the four epilogue warps of a sub-partition two then always hold the 16-column group with the
+//      logarithm and two the one without; the pair with the logarithm becomes the critical path (the issuer waits 1100 cycles
+//      per tile for their accumulator buffer, against 340-400 in the shipped layout) while the other two idle.
+//   -DIPN_TC_INTERLEAVE=3: as 2, the halves swapping every other pair of tiles (every warp alternates): 3-5 % slower.
 // tc_bin_position: position in the permuted order of the bin with rank r within its class (n_nz bins with counts among T).
 #ifndef IPN_TC_INTERLEAVE
 #define IPN_TC_INTERLEAVE 1
 #endif
 __device__ __forceinline__ long long tc_bin_position(bool has_counts, long long r, long long n_nz, long long T, int TN) {
+    if (IPN_TC_INTERLEAVE >= 2) {
+        const long long H = TN / 2, n_z = T - n_nz;
+        const long long M = (n_nz < n_z ? n_nz : n_z) / H;  // mixed tiles
+        if (r < M * H) {
+            const long long j = r / H;
+            const bool upper = IPN_TC_INTERLEAVE == 3 ? (has_counts == (((j >> 1) & 1) != 0)) : !has_counts;
+            return j * TN + (upper ? H : 0) + r % H;
+        }
+        return M * TN + (has_counts ? 0 : n_nz - M * H) + (r - M * H);
+    }
     const long long Tc = (n_nz + TN - 1) / TN;   // tiles that start with a bin with counts
     const long long hole = Tc * TN - n_nz;       // rows of the last of them that bins without counts fill up
     const long long n_z = T - n_nz;
@@ -140,14 +159,20 @@ __device__ __forceinline__ float exp2_core_df(float xf, float t, float& lo) {
 // kLevel6Half: S5 arrives with the level-6 sum folded in by an arithmetic shift (fold_level6, loglik_epilogue.cuh), i.e. half a
 // level-5 unit too low on average; the half goes back in through the addend of the conversion's FMA (no extra instruction).
 constexpr float kLevel6Half = 0.5f;
-__device__ __forceinline__ float exponent_parts(int s2, int s3, int s4, int s5, int sh, float inv, float ks24, int& k) {
-    const int H = s2 * 256 + s3;
+// The two integers the assembly works on.  The epilogue threads form them right behind the tensor-memory loads, which halves the
+// registers the accumulators of a work unit occupy while the unit before it is in flight (loglik_tc.cu).
+__device__ __forceinline__ int levels_high(int s2, int s3) { return s2 * 256 + s3; }
+__device__ __forceinline__ int levels_low(int s4, int s5) { return s4 * 256 + s5; }
+__device__ __forceinline__ float exponent_parts_hl(int H, int L, int sh, float inv, float ks24, int& k) {
     k = (H + (1 << (sh - 1))) >> sh;
     const int fr = H - (k << sh);
     // the half unit rides in the FMA of the LOW levels: their product has a full mantissa of pseudo-random bits, so the tiny
     // addend survives the rounding on average; behind the exact fr 2^-sh (few significant bits) it would be rounded away every
     // time (measured in the emulation: a bias of -0.5 ks 2^-24 in x)
-    return fmaf((float)fr, inv, fmaf((float)(s4 * 256 + s5), ks24, kLevel6Half * ks24));  // inv = 2^-sh
+    return fmaf((float)fr, inv, fmaf((float)L, ks24, kLevel6Half * ks24));  // inv = 2^-sh
+}
+__device__ __forceinline__ float exponent_parts(int s2, int s3, int s4, int s5, int sh, float inv, float ks24, int& k) {
+    return exponent_parts_hl(levels_high(s2, s3), levels_low(s4, s5), sh, inv, ks24, k);
 }
 // e^(xf ln 2) 2^k, |xf| <= 0.54, |k| <= 120
 __device__ __forceinline__ float exp2_parts(float xf, int k) {

@@ -37,8 +37,16 @@ __device__ __forceinline__ int fold_level6(int s5, int s6) { return s5 + (s6 >> 
 
 // Eight consecutive bins (TMEM columns) of one delay (TMEM lane): exponent assembly, Poisson terms, compensated sum.
 // HC = the tile holds bins with counts > 0 (log needed); all-zero tiles only need -kappa u.
+// The units take the levels either as four arrays (S2 .. S5) or already combined into H = 256 S2 + S3 and L = 256 S4 + S5
+// (levels_high / levels_low): the same integers either way.
+#define IPN_COMBINE_LEVELS8(H, L)                    \
+    int H[8], L[8];                                  \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) { \
+        H[j] = levels_high(s2[j], s3[j]);            \
+        L[j] = levels_low(s4[j], s5[j]);             \
+    }
 template <bool HC>
-__device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+__device__ __forceinline__ void epi_units8(const int (&H)[8], const int (&L)[8],
                                            const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp, float& slo) {
     float v[8];
 #pragma unroll
@@ -46,7 +54,7 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
         const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
         // x = ks (S2 + 2^-8 S3 + 2^-16 S4 + 2^-24 S5): integer part and fraction from the integers (exponent_parts)
         int k;
-        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        const float xf = exponent_parts_hl(H[j], L[j], sh, inv, ks24, k);
         const float u = exp2_parts(xf, k);
         if (HC) {
             float l;
@@ -68,15 +76,26 @@ __device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8
     }
 }
 
+template <bool HC>
+__device__ __forceinline__ void epi_units8(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                           const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp, float& slo) {
+    IPN_COMBINE_LEVELS8(H, L)
+    epi_units8<HC>(H, L, cst, sh, inv, ks24, ssum, scomp, slo);
+}
+
 // Store epilogue (ipn_rff_eval on uniform bins through the same contraction): no Poisson terms, just u = 2^x of the eight bins.
-__device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
-                                                 int sh, float inv, float ks24, float (&u)[8]) {
+__device__ __forceinline__ void epi_units8_store(const int (&H)[8], const int (&L)[8], int sh, float inv, float ks24, float (&u)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int k;
-        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        const float xf = exponent_parts_hl(H[j], L[j], sh, inv, ks24, k);
         u[j] = exp2_parts(xf, k);
     }
+}
+__device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                                 int sh, float inv, float ks24, float (&u)[8]) {
+    IPN_COMBINE_LEVELS8(H, L)
+    epi_units8_store(H, L, sh, inv, ks24, u);
 }
 
 // Compensated fp32 epilogue for moderately bright data (tens of counts per bin).  What limits the plain version there is
@@ -90,14 +109,14 @@ __device__ __forceinline__ void epi_units8_store(const int (&s2)[8], const int (
 // the TwoSum of the difference (3 instructions per bin less than summing d = n y0 - kappa u with one Kahan step) and gives
 // two independent dependency chains.  The caller forms (ssum - scomp) - (qsum - qcomp) + slo in float64 per work item.
 template <bool HC>
-__device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+__device__ __forceinline__ void epi_units8_comp(const int (&H)[8], const int (&L)[8],
                                                 const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp,
                                                 float& qsum, float& qcomp, float& slo) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];  // warp-uniform (n, kappa_hi, kappa_lo, n log2e)
         int k;
-        const float xf = exponent_parts(s2[j], s3[j], s4[j], s5[j], sh, inv, ks24, k);
+        const float xf = exponent_parts_hl(H[j], L[j], sh, inv, ks24, k);
         float ul;  // u = 2^x as hi + lo
         const float u = exp2_parts_df(xf, k, ul);
         // kappa u = q + (eq + klo u + khi ul), q = fl(khi u)
@@ -130,19 +149,32 @@ __device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&
     }
 }
 
+template <bool HC>
+__device__ __forceinline__ void epi_units8_comp(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8], const int (&s5)[8],
+                                                const float4* __restrict__ cst, int sh, float inv, float ks24, float& ssum, float& scomp,
+                                                float& qsum, float& qcomp, float& slo) {
+    IPN_COMBINE_LEVELS8(H, L)
+    epi_units8_comp<HC>(H, L, cst, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
+}
+
 // fp64 epilogue for bright / coarsely binned data (hundreds of counts per bin): the fp32 terms above carry
 // ~6e-8 n_i relative noise each, which exceeds 1e-3 nats once sum n_i^2 is large.  4-5x slower, selected per draw.
-__device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8],
-                                                const int (&s5)[8], const float4* __restrict__ cst, double ksd, double& acc) {
+__device__ __forceinline__ void epi_units8_hifi(const int (&H)[8], const int (&L)[8], const float4* __restrict__ cst, double ksd, double& acc) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 c = cst[j];
-        const double x = ksd * ((double)s2[j] + 0.00390625 * (double)s3[j] +
-                                5.9604644775390625e-8 * ((double)s4[j] * 256.0 + (double)s5[j] + (double)kLevel6Half));
+        // S2 + 2^-8 S3 = 2^-8 H and 256 S4 + S5 = L, all exact in float64
+        const double x = ksd * (0.00390625 * (double)H[j] + 5.9604644775390625e-8 * ((double)L[j] + (double)kLevel6Half));
         const double u = exp2(x);
         const double kap = (double)c.y + (double)c.z;
         acc += (double)c.x * (log1p(u) * kLog2e) - kap * u;
     }
+}
+
+__device__ __forceinline__ void epi_units8_hifi(const int (&s2)[8], const int (&s3)[8], const int (&s4)[8],
+                                                const int (&s5)[8], const float4* __restrict__ cst, double ksd, double& acc) {
+    IPN_COMBINE_LEVELS8(H, L)
+    epi_units8_hifi(H, L, cst, ksd, acc);
 }
 
 }  // namespace ipn

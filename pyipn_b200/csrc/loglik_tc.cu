@@ -555,11 +555,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                 mbar_wait_timed(t_full + tile_seq % NTF, (tile_seq / NTF) & 1, w_tf, dbg, W_T_FULL, tile_seq, prog);
                 tc_fence_after();
                 const float4* cbase = reinterpret_cast<const float4*>(sC0 + (size_t)cs * CONST_BYTES);
-                const bool has_counts = cbase[TN].x != 0.0f;
+                const float* unit_flag = reinterpret_cast<const float*>(cbase + TN);  // one per 8 bins: the unit holds bins with counts
                 for (; cg < GROUPS; cg += EPI_SLOTS) {
                     const float4* cst = cbase + cg * GCOLS;
                     const uint32_t t0 = tmem_base + ACC_COL0 + lane_addr + tb * (NLEV * TN) + cg * GCOLS;
-                    int acc[NH][NLEV][8];
+                    // The accumulators leave this block as TWO integers per bin, H = 256 S2 + S3 and L = 256 S4 + S5 (levels_high /
+                    // levels_low, the operands of the exponent assembly): 32 registers for the 16 bins instead of 64, so the
+                    // second unit's values do not crowd the registers while the first unit's eight bins are interleaved.
+                    static_assert(NLEV == 4, "levels 2 .. 5, level 6 folded into level 5");
+                    int hi[NH][8], lo[NH][8];
                     // Two rounds of tensor-memory loads so that no more than 64 accumulator registers are live at once.
                     // First the lowest level and level 6 (weight 2^-8 of it, single-buffered): fold, and hand the level-6
                     // columns back at once -- the issuer of the NEXT tile waits for them.
@@ -572,20 +576,20 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                             tc_wait_ld();
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                acc[0][NLEV - 1][j] = fold_level6(v[j], acc6[j]);
-                                acc[NH - 1][NLEV - 1][j] = fold_level6(v[8 + j], acc6[8 + j]);
+                                lo[0][j] = fold_level6(v[j], acc6[j]);
+                                lo[NH - 1][j] = fold_level6(v[8 + j], acc6[8 + j]);
                             }
                         } else {
 #pragma unroll
                             for (int h = 0; h < NH; ++h) {
-                                tc_ld8(t0 + (NLEV - 1) * TN + h * 8, acc[h][NLEV - 1]);
+                                tc_ld8(t0 + (NLEV - 1) * TN + h * 8, lo[h]);
                                 tc_ld8(tmem_base + L6_COL0 + lane_addr + cg * GCOLS + h * 8, reinterpret_cast<int(&)[8]>(acc6[h * 8]));
                             }
                             tc_wait_ld();
 #pragma unroll
                             for (int h = 0; h < NH; ++h)
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) acc[h][NLEV - 1][j] = fold_level6(acc[h][NLEV - 1][j], acc6[h * 8 + j]);
+                                for (int j = 0; j < 8; ++j) lo[h][j] = fold_level6(lo[h][j], acc6[h * 8 + j]);
                         }
                         tc_fence_before();
                         __syncwarp();
@@ -593,23 +597,35 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                     }
                     if (NH == 2) {
                         // one 16-column load per level instead of two 8-column ones
+                        int v2[16], v3[16], v4[16];
+                        tc_ld16(t0, v2);
+                        tc_ld16(t0 + TN, v3);
+                        tc_ld16(t0 + 2 * TN, v4);
+                        tc_wait_ld();
 #pragma unroll
-                        for (int lev = 0; lev < NLEV - 1; ++lev) {
-                            int v[16];
-                            tc_ld16(t0 + lev * TN, v);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                acc[0][lev][j] = v[j];
-                                acc[NH - 1][lev][j] = v[8 + j];
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            hi[0][j] = levels_high(v2[j], v3[j]);
+                            hi[NH - 1][j] = levels_high(v2[8 + j], v3[8 + j]);
+                            lo[0][j] = levels_low(v4[j], lo[0][j]);
+                            lo[NH - 1][j] = levels_low(v4[8 + j], lo[NH - 1][j]);
                         }
                     } else {
+                        int v2[NH][8], v3[NH][8], v4[NH][8];
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            tc_ld8(t0 + h * 8, v2[h]);
+                            tc_ld8(t0 + TN + h * 8, v3[h]);
+                            tc_ld8(t0 + 2 * TN + h * 8, v4[h]);
+                        }
+                        tc_wait_ld();
 #pragma unroll
                         for (int h = 0; h < NH; ++h)
 #pragma unroll
-                            for (int lev = 0; lev < NLEV - 1; ++lev) tc_ld8(t0 + lev * TN + h * 8, acc[h][lev]);
+                            for (int j = 0; j < 8; ++j) {
+                                hi[h][j] = levels_high(v2[h][j], v3[h][j]);
+                                lo[h][j] = levels_low(v4[h][j], lo[h][j]);
+                            }
                     }
-                    tc_wait_ld();
                     // this (quarter, group) of the accumulator buffer is in registers: hand it back before the math
                     tc_fence_before();
                     __syncwarp();
@@ -623,14 +639,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
 #pragma unroll
                         for (int h = 0; h < NH; ++h)
 #pragma unroll
-                            for (int lev = 0; lev < NLEV; ++lev) x ^= acc[h][lev][(h + lev) & 7];
+                            for (int lev = 0; lev < NLEV; ++lev) x ^= (lev & 1 ? hi : lo)[h][(h + lev) & 7];
                         slo += __int_as_float(x) * 0.0f;
                     } else {
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
+                            const bool has_counts = unit_flag[(cg * GCOLS) / 8 + h] != 0.0f;  // warp-uniform
                             if (MODE == EPI_STORE) {
                                 float u8[8];
-                                epi_units8_store(acc[h][0], acc[h][1], acc[h][2], acc[h][3], sh, inv, ks24, u8);
+                                epi_units8_store(hi[h], lo[h], sh, inv, ks24, u8);
                                 // bin i = p Q + q: p = the column's position among the "bins", q = this thread's "delay" row;
                                 // for one column the 32 lanes of the warp write 256 consecutive bytes
                                 const int64_t q = (int64_t)dt * TM + quarter * 32 + lane;
@@ -642,17 +659,17 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) loglik_tc_kernel(const TcPara
                                     if (q < p.out_Q && i < p.out_T) orow[i] = sgn * (double)u8[j];
                                 }
                             } else if (MODE == EPI_FP64)
-                                epi_units8_hifi(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, ksd, hacc);
+                                epi_units8_hifi(hi[h], lo[h], cst + 8 * h, ksd, hacc);
                             else if (MODE == EPI_COMP && has_counts)
-                                epi_units8_comp<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
+                                epi_units8_comp<true>(hi[h], lo[h], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
                             else if (MODE == EPI_COMP && zero_plain)  // bins without counts: - kappa u is small unless the model is grossly off
-                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
+                                epi_units8<false>(hi[h], lo[h], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                             else if (MODE == EPI_COMP)
-                                epi_units8_comp<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
+                                epi_units8_comp<false>(hi[h], lo[h], cst + 8 * h, sh, inv, ks24, ssum, scomp, qsum, qcomp, slo);
                             else if (has_counts)
-                                epi_units8<true>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
+                                epi_units8<true>(hi[h], lo[h], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                             else
-                                epi_units8<false>(acc[h][0], acc[h][1], acc[h][2], acc[h][3], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
+                                epi_units8<false>(hi[h], lo[h], cst + 8 * h, sh, inv, ks24, ssum, scomp, slo);
                         }
                     }
                     __syncwarp();

@@ -43,7 +43,8 @@ constexpr int MMA_WARP = EPI_WARPS + 1;       // 17: issues the even tiles (accu
 constexpr int MMA_WARP2 = EPI_WARPS + 2;      // 18: issues the odd tiles (accumulator buffer 1) from another sub-partition
 constexpr int KPAD_MAX = 224;
 constexpr int MIN_CROWS = 8;  // K rows reserved for the additive constant
-constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one (tile flag, -, -, -) block
+constexpr int CONST_BYTES = TN * 16 + 16;  // per-bin (n, kappa_hi, kappa_lo, n log2e) + one block of flags, one per 8 bins
+static_assert(TN % 16 == 0 && TN / 8 <= 4, "the flag block holds four floats: one per 8 bins of a tile; tc_bin_position mixes halves of a tile");
 // A parity wait on an mbarrier is only sound if the waiter sees EVERY phase of that barrier (it cannot tell "two phases
 // away" from "done").  A warp of epilogue slot s owns the groups with (GROUPS tile + g) % EPI_SLOTS == s, so it skips tiles
 // (every other one with 4 slots and 2 groups, every third with 3 slots); with two MMA issuers tiles may also complete out
@@ -311,14 +312,10 @@ __global__ void __launch_bounds__(256) tc_pimg_kernel(int64_t S0, int J, int Kpa
             c.z = (float)(kap - (double)khi);
             c.w = c.x * 1.44269504f;  // n log2e, multiplies the log correction term
             *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)row * 16) = c;
-            if (row == 0) {
-                float4 f;
-                // the tile holds at least one bin with counts: its first bin does (tiles are homogeneous up to the one boundary
-                // tile, which starts with the last bins with counts; the thread of row 0 is here and has the tile's first bin in i)
-                f.x = (valid && counts[i] > 0) ? 1.0f : 0.0f;
-                f.y = f.z = f.w = 0.0f;
-                *reinterpret_cast<float4*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16) = f;
-            }
+            // one flag per 8 rows (= per epilogue unit): the unit holds at least one bin with counts iff its first bin does (within
+            // any 8 rows the bins with counts come first, tc_bin_position); the unit's first thread has that bin in i
+            if ((row & 7) == 0)
+                reinterpret_cast<float*>(img + (size_t)tc::PP * b_plane + (size_t)tc::TN * 16)[row >> 3] = (valid && counts[i] > 0) ? 1.0f : 0.0f;
         }
     }
 }

@@ -61,12 +61,28 @@ int main(int argc, char** argv) {
         return 0;
     };
 
-    // expected order, built tile by tile (independently of tc_bin_position's closed form): bins with counts and bins without,
-    // each class in its original order; the last tile of the first class is filled up with the first bins of the second; of
-    // the FULL tiles of both classes the first m = min(#full C, #full Z) are laid out C Z Z C | C Z Z C | ..., the rest follows
-    // in natural order (all remaining C tiles, then the remaining Z tiles, a partial one last)
+    // expected order, built tile by tile (independently of tc_bin_position's closed form) from the two classes -- bins with
+    // counts and bins without, each in its original order
     std::vector<int> cls_c, cls_z;
     for (int64_t i = 0; i < T; ++i) (counts[i] > 0 ? cls_c : cls_z).push_back((int)i);
+    std::vector<int> want;
+#if IPN_TC_INTERLEAVE >= 2
+    // mixed tiles while both classes last: 16 bins with counts in one half of the tile and 16 without in the other (mode 3:
+    // the halves swap every other pair of tiles); then the rest of the bins with counts, then the rest of those without
+    const size_t M = std::min(cls_c.size(), cls_z.size()) / 16;
+    for (size_t j = 0; j < M; ++j) {
+        const bool swap = IPN_TC_INTERLEAVE == 3 && ((j >> 1) & 1);
+        const std::vector<int>& lo = swap ? cls_z : cls_c;
+        const std::vector<int>& hi = swap ? cls_c : cls_z;
+        want.insert(want.end(), lo.begin() + 16 * j, lo.begin() + 16 * j + 16);
+        want.insert(want.end(), hi.begin() + 16 * j, hi.begin() + 16 * j + 16);
+    }
+    want.insert(want.end(), cls_c.begin() + 16 * M, cls_c.end());
+    want.insert(want.end(), cls_z.begin() + 16 * M, cls_z.end());
+#else
+    // homogeneous tiles: the last tile of the first class is filled up with the first bins of the second; of
+    // the FULL tiles of both classes the first m = min(#full C, #full Z) are laid out C Z Z C | C Z Z C | ..., the rest follows
+    // in natural order (all remaining C tiles, then the remaining Z tiles, a partial one last)
     std::vector<std::vector<int>> tc_tiles, tz_tiles;
     size_t zi = 0;
     for (size_t k = 0; k < cls_c.size(); k += 32) tc_tiles.emplace_back(cls_c.begin() + k, cls_c.begin() + std::min(cls_c.size(), k + 32));
@@ -84,8 +100,8 @@ int main(int argc, char** argv) {
     }
     for (size_t j = m; j < tc_tiles.size(); ++j) order.push_back(tc_tiles[j]);
     for (size_t j = m; j < tz_tiles.size(); ++j) order.push_back(tz_tiles[j]);
-    std::vector<int> want;
     for (auto& t : order) want.insert(want.end(), t.begin(), t.end());
+#endif
     if ((int64_t)want.size() != T) {
         std::printf("expected order has %zu entries for T = %lld\n", want.size(), (long long)T);
         return 1;

@@ -393,9 +393,9 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                 for (int k = 0; k < Kpad; ++k)
                     img[pl * b_plane + ((size_t)(k / 16) * cfg::TN + row) * 16 + k % 16] = (uint8_t)P[((size_t)pl * Tpad + pos) * Kpad + k];
             std::memcpy(img + 4 * b_plane + (size_t)row * 16, &cst[pos], 16);
-            if (row == 0) {
-                const float4 fl = {counts[perm[pos]] > 0 ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
-                std::memcpy(img + 4 * b_plane + (size_t)cfg::TN * 16, &fl, 16);
+            if (row % 8 == 0) {  // one flag per 8 rows: the unit's first bin holds counts
+                const float fl = (pos < T && counts[perm[pos]] > 0) ? 1.0f : 0.0f;
+                std::memcpy(img + 4 * b_plane + (size_t)cfg::TN * 16 + (row / 8) * 4, &fl, 4);
             }
         }
         FILE* g = std::fopen(dump_path, "wb");
@@ -424,7 +424,6 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
             double hacc[cfg::EPI_SLOTS] = {};
             unsigned tile_seq = 0;
             for (int bt = bt0; bt < bt1; ++bt, ++tile_seq) {
-                const bool has_counts = counts[perm[(size_t)bt * cfg::TN]] > 0;  // the tile's first bin (tc_pimg_kernel's flag)
                 // the eleven digit-plane products of the tile (int32, exact), loglik_tc.cu header
                 for (int r = 0; r < cfg::TN; ++r) {
                     const size_t pos = (size_t)bt * cfg::TN + r;
@@ -458,6 +457,9 @@ static int run_grid(const char* path, double bias, double noise, const char* dum
                             t5[j] = S5[o + j];
                         }
                         const float4* cp = &cst[(size_t)bt * cfg::TN + o];
+                        // the unit's first bin holds counts (tc_pimg_kernel's flag, one per 8 rows)
+                        const size_t p0 = (size_t)bt * cfg::TN + o;
+                        const bool has_counts = (int64_t)p0 < T && counts[perm[p0]] > 0;
                         if (has_counts) {
                             epi_units8<true>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[0][slot], scomp[0][slot], slo[0][slot]);
                             epi_units8_comp<true>(t2, t3, t4, t5, cp, sh, inv, ks24, ssum[1][slot], scomp[1][slot], qsum[slot], qcomp[slot], slo[1][slot]);

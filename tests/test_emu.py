@@ -267,9 +267,9 @@ def test_rff_phase_beyond_the_fp32_reduction_takes_the_fp64_path(emu, tmp_path):
 def perm_emu():
     src = os.path.join(HERE, "emu", "perm_emu.cpp")
     exe = os.path.join(BUILD, "perm_emu")
-    hdr = os.path.join(HERE, "..", "pyipn_b200", "csrc", "tc_perm.cuh")
+    hdrs = [os.path.join(HERE, "..", "pyipn_b200", "csrc", h) for h in ("tc_perm.cuh", "loglik_common.cuh")]
     os.makedirs(BUILD, exist_ok=True)
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(p) for p in [src, *hdrs]):
         subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-o", exe, src], check=True)
     return exe
 
