@@ -1,9 +1,9 @@
 #!/bin/bash
-# A/B on one box: the shipped library against variants (libipn_b200_<tag>.so): old = the build before levels were combined behind the
-# tensor-memory loads, il2 / il3 = mixed tiles (-DIPN_TC_INTERLEAVE=2 | 3).
+# A/B on one box: the shipped library against variants built with IPN_BUILD_TAG=<tag> IPN_NVCC_EXTRA=... python -m pyipn_b200._build
+# (libipn_b200_<tag>.so): il2 / il3 = mixed tiles (-DIPN_TC_INTERLEAVE=2 | 3).  A missing variant prints "no line".
 mkdir -p gpurun_out/mixed; O=gpurun_out/mixed
 timeout 600 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.txt
-for v in default old il2 il3 default old il2 il3; do
+for v in default il2 il3 default il2 il3; do  # add further tags (e.g. a build of an older commit) as needed
   if [ $v = default ]; then unset IPN_B200_LIB; else export IPN_B200_LIB=$PWD/pyipn_b200/libipn_b200_$v.so; fi
   timeout 300 python bench.py --draws 500 --steps 3 --warmup 2 --no-cpu-baseline > $O/bench_$v.json 2> $O/bench_$v.err; rc=$?
   python - $v $rc <<'PY'
