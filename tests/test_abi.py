@@ -27,6 +27,15 @@ def test_header_and_binding_agree():
     assert declared_symbols() == sorted(_lib.EXPORTS)
 
 
+def test_integration_guide_names_every_entry_point_and_option():
+    """INTEGRATION.md is the maintainer's map from reference call sites to entry points: every function of the header and
+    every IPN_OPT_* name appears there."""
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    header = open(os.path.join(ROOT, "include", "ipn.h")).read()
+    names = declared_symbols() + sorted(set(re.findall(r"\b(IPN_OPT_[A-Z0-9_]+)\b", header)))
+    assert [n for n in names if n not in guide] == []
+
+
 def test_library_exports_every_declared_symbol(lib):
     for name in declared_symbols():
         assert hasattr(lib, name), name
