@@ -284,6 +284,19 @@ def test_permutation_kernels_run_from_their_own_source(perm_emu, T, seed, mean):
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("layout", [0, 2, 3])
+def test_alternative_bin_layouts_are_permutations_too(layout, tmp_path):
+    """The bin orders kept as build options (-DIPN_TC_INTERLEAVE=0 natural, 2 / 3 bins with and without counts mixed within
+    every tile; measured slower, profiles/r02_tile_layouts_ab.txt) stay correct: the permutation kernel compiled with the
+    option reproduces the order built tile by tile, for sparse, balanced and bright data and a partial last tile."""
+    src = os.path.join(HERE, "emu", "perm_emu.cpp")
+    exe = str(tmp_path / f"perm_emu_{layout}")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", f"-DIPN_TC_INTERLEAVE={layout}", "-o", exe, src], check=True)
+    for T, seed, mean in [(0, 1, 0.9), (31, 3, 0.9), (1025, 5, 2.0), (4100, 6, 0.8), (3333, 7, 0.1), (2500, 8, 6.0), (64, 10, 0.7)]:
+        r = subprocess.run([exe, str(T), str(seed), str(mean)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), (layout, T, r.stdout + r.stderr)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the operand-image kernels themselves (tc_images.cuh + tc_perm.cuh) on the host, against the restatement used above
 # ---------------------------------------------------------------------------------------------------------------
